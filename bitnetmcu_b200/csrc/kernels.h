@@ -1,0 +1,51 @@
+// kernels.h -- internal launch interface between the C-ABI layer (capi.cu) and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace bnm {
+
+constexpr int kMaxFcLayers = 8;
+constexpr int kTileM = 128;  // images per MMA tile / per CTA tile of the layer kernels
+
+// One fully connected layer, decoded once at model build into dense int8 planes (K3 "weight pre-decode").
+struct FcLayerDev {
+    int32_t enc = 0;
+    uint32_t n_in = 0, n_out = 0;   // as in the model header (Lk_incoming_weights / Lk_outgoing_weights)
+    uint32_t k_pad = 0;             // n_in rounded up to 32 (one tcgen05 kind::i8 K-step), zero padded
+    uint32_t n_pad = 0;             // n_out rounded up to 16 (UMMA N granularity), zero padded
+    int8_t *dense_a = nullptr;      // [n_pad][k_pad] row-major int8: clamp(w, -128, 127)
+    int8_t *dense_b = nullptr;      // [n_pad][k_pad] residual plane w - clamp(w) (only FP130's +128), or null
+    int4 *quad_a = nullptr;         // dp4a layout [(n_pad/4)][k_pad/4] of int4 = 4 outputs x 4 k (layer kernels)
+    int4 *quad_b = nullptr;
+};
+
+// ---- weight decode (packed exportquant words -> dense planes); returns whether plane B is needed via *d_flag
+void launch_decode_fc(const void *d_packed, int32_t enc, uint32_t n_in, uint32_t n_out, uint32_t k_pad, uint32_t n_pad,
+                      int8_t *dense_a, int8_t *dense_b, int4 *quad_a, int4 *quad_b, int nf4_extension, int *d_flag,
+                      cudaStream_t st);
+
+// ---- layer-by-layer CUDA-core path (any shape)
+// act int8 [n][act_stride] (zero padded to >= k_pad) -> out int32 [n][n_out]
+void launch_fc_dp4a(const int8_t *act, uint32_t act_stride, const FcLayerDev &L, int32_t *out, size_t n, cudaStream_t st);
+// in int32 [n][n_in] -> out int8 [n][out_stride] (zero padded), argmax uint32 [n]; out / argmax may be null
+void launch_relunorm(const int32_t *in, uint32_t n_in, int8_t *out, uint32_t out_stride, uint32_t *argmax, size_t n,
+                     cudaStream_t st);
+void launch_conv33relu(const int32_t *act, const int8_t *w, uint32_t n_w, uint32_t xy, uint32_t n_shift, int32_t *out,
+                       size_t n, cudaStream_t st);
+void launch_maxpool22(const int32_t *act, uint32_t xy, int32_t *out, size_t n, cudaStream_t st);
+// fused CNN front-end (dll.c:64-80): images int8 [n][256] -> features int8 [n][feat_stride] after ReLUNorm over C*4
+// returns false if the geometry is not the 16x16 / conv,conv,pool,conv,pool one
+bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
+                         uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, cudaStream_t st);
+
+// ---- fused tcgen05 FC chain (fc_tcgen05.cu)
+struct FcChainPlan;  // opaque, owned by the model
+FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32_t in_bytes, int device, int sm_count,
+                                  char *err, size_t err_len);
+void fc_chain_plan_destroy(FcChainPlan *p);
+// images int8 [n][in_bytes] (device, 16B aligned) -> logits int32 [n][n_classes], labels uint32 [n] (may be null)
+int fc_chain_launch(FcChainPlan *p, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st);
+
+}  // namespace bnm
