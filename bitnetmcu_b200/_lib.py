@@ -1,0 +1,79 @@
+"""ctypes loader for the C-ABI library (bitnetmcu_b200/libbitnetmcu_b200.so, built in-tree by csrc/Makefile).
+
+There is no Python or CPU implementation behind this module: if the CUDA library is missing the import of
+anything that computes fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbitnetmcu_b200.so")
+
+# every symbol include/bitnetmcu_b200.h declares (checked by tests/test_capi_symbols.py)
+EXPORTED = [
+    "ReLUNorm", "processfclayer", "processconv33ReLU", "processmaxpool22",
+    "bnm_version", "bnm_last_error", "bnm_device_count",
+    "bnm_model_create", "bnm_model_load_blob", "bnm_model_destroy", "bnm_model_n_classes", "bnm_model_img_bytes",
+    "bnm_model_set_option", "bnm_model_get_option", "bnm_model_active_path",
+    "bnm_infer_batch", "bnm_infer_batch_device", "bnm_infer_launch_count", "bnm_host_alloc", "bnm_host_free",
+    "bnm_processfclayer_batch", "bnm_relunorm_batch", "bnm_conv33relu_batch", "bnm_maxpool22_batch",
+]
+
+PATH_AUTO, PATH_LAYERS, PATH_TCGEN05 = 0, 1, 2
+OPT_PATH, OPT_NF4_EXTENSION, OPT_CHUNK_IMAGES = 1, 2, 3
+
+
+class BnmLayer(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("bitperweight", C.c_int32), ("n_in", C.c_uint32), ("n_out", C.c_uint32),
+                ("in_channels", C.c_uint32), ("groups", C.c_uint32), ("weights", C.c_void_p), ("weight_bytes", C.c_size_t)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library (once).  Raises if it has not been built: the product path has no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a).  bitnetmcu_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, i32, sz, i64 = C.c_void_p, C.c_uint32, C.c_int32, C.c_size_t, C.c_int64
+    sig = {
+        "bnm_version": (C.c_int, []), "bnm_last_error": (C.c_char_p, []), "bnm_device_count": (C.c_int, []),
+        "bnm_model_create": (C.c_int, [C.c_int, C.POINTER(BnmLayer), u32, u32, C.c_int, C.POINTER(vp)]),
+        "bnm_model_load_blob": (C.c_int, [vp, sz, C.c_int, C.POINTER(vp)]),
+        "bnm_model_destroy": (None, [vp]),
+        "bnm_model_n_classes": (u32, [vp]), "bnm_model_img_bytes": (u32, [vp]),
+        "bnm_model_set_option": (C.c_int, [vp, C.c_int, i64]), "bnm_model_get_option": (i64, [vp, C.c_int]),
+        "bnm_model_active_path": (C.c_int, [vp]),
+        "bnm_infer_batch": (C.c_int, [vp, vp, sz, vp, vp]),
+        "bnm_infer_batch_device": (C.c_int, [vp, vp, sz, vp, vp, vp]),
+        "bnm_infer_launch_count": (C.c_int, [vp, sz]),
+        "bnm_host_alloc": (vp, [sz]), "bnm_host_free": (None, [vp]),
+        "bnm_processfclayer_batch": (C.c_int, [vp, vp, i32, u32, u32, vp, sz, C.c_int]),
+        "bnm_relunorm_batch": (C.c_int, [vp, vp, vp, u32, sz]),
+        "bnm_conv33relu_batch": (C.c_int, [vp, vp, u32, u32, u32, vp, sz]),
+        "bnm_maxpool22_batch": (C.c_int, [vp, u32, vp, sz]),
+        "ReLUNorm": (u32, [vp, vp, u32]),
+        "processfclayer": (None, [vp, vp, i32, u32, u32, vp]),
+        "processconv33ReLU": (vp, [vp, vp, u32, u32, vp]),
+        "processmaxpool22": (vp, [vp, u32, vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+class BnmError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise BnmError(f"{what} failed (rc={rc}): {load().bnm_last_error().decode(errors='replace')}")

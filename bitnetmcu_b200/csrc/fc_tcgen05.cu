@@ -1,0 +1,431 @@
+// fc_tcgen05.cu -- the hot path: the whole processfclayer -> ReLUNorm chain of BitMnistInference
+// (/root/reference/BitNetMCU_MNIST_dll.c:95-121, kernels inference.c:88-208 + 23-72) as ONE persistent
+// sm_100a kernel.  Per 128-image tile:
+//
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B, evict-first)  images  HBM -> smem ring        [producer warp]
+//   layer 1   tcgen05.mma kind::i8  A = smem image tile, B = decoded int8 weights (smem)  -> D int32 in TMEM
+//   ReLUNorm  tcgen05.ld (thread = image row): max -> shift -> clamp(x+r,0,cap)>>shift -> int8x4 pack
+//             -> tcgen05.st back into TMEM as the next layer's A operand (no smem / HBM round trip)
+//   layer l>1 tcgen05.mma kind::i8  A = TMEM (.ts form), B = smem weights                 -> D int32 in TMEM
+//   last      int32 logits: thread-local argmax (first maximum) -> smem staging -> one cp.async.bulk store
+//
+// Several warpgroups (128 threads = 128 TMEM lanes each) run this chain on different tiles so the tensor
+// pipe, the TMEM<->register traffic and the integer ALU work of the ReLUNorm epilogues overlap.
+// Weights of every encoding are pre-decoded once per model into int8 planes (kernels.h FcLayerDev); FP130's
+// +128 does not fit s8 and is carried by a second residual plane accumulated by extra MMAs into the same D.
+// All arithmetic is integer: results are bit-exact with the reference.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace bnm {
+
+constexpr int kMaxWG = 4;
+constexpr int kMaxStages = 8;
+
+struct ChainParams {
+    int n_layers;
+    uint32_t n_pad[kMaxFcLayers];     // UMMA N of layer l (multiple of 16)
+    uint32_t n_real[kMaxFcLayers];    // real outputs
+    uint32_t k_steps[kMaxFcLayers];   // K/32 MMA steps per plane
+    uint32_t planes[kMaxFcLayers];    // 1, or 2 when the residual plane exists
+    uint32_t b_off[kMaxFcLayers];     // smem byte offset (from weight base) of the layer's first [n_pad x 32B] tile
+    uint32_t idesc[kMaxFcLayers];
+    uint32_t in_atoms;                // layer-1 A: 128-byte SW128 atoms per row (TMA boxes per tile)
+    uint32_t stage_bytes;             // in_atoms * 128 rows * 128 B
+    uint32_t n_stages, n_wg;
+    uint32_t w_bytes;                 // weight image bytes (multiple of 16)
+    uint32_t off_w, off_out;          // smem offsets (from the 1024-aligned base): weights, per-WG logits staging
+    uint32_t out_stage_bytes;         // per-WG staging bytes = 128 * n_classes * 4
+    uint32_t tmem_wg_cols, tmem_a_off;
+    uint32_t n_classes;
+    uint32_t n_tiles;
+    const uint8_t *w_image;
+    int32_t *logits;
+    uint32_t *labels;
+    size_t n;
+    int *err;
+};
+
+struct FcChainPlan {
+    ChainParams p{};
+    uint8_t *d_w_image = nullptr;
+    int *d_err = nullptr;
+    size_t smem_bytes = 0;
+    uint32_t in_bytes = 0;
+    int threads = 0;
+    int sm_count = 0;
+    int device = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// weight image: every MMA K-step reads one [n_pad x 32 B] tile in the no-swizzle K-major canonical layout
+// (8-row x 16-byte core matrices; LBO = 128 B between the two K halves, SBO = 256 B between 8-row groups)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_build_b_image(const int8_t *__restrict__ dense, uint32_t k_pad_src, uint32_t n_pad, uint32_t k_steps,
+                                uint8_t *__restrict__ image) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)n_pad * k_steps * 32;
+    if (idx >= total) return;
+    uint32_t n = idx / (k_steps * 32), k = idx % (k_steps * 32);
+    uint8_t v = k < k_pad_src ? (uint8_t)dense[(size_t)n * k_pad_src + k] : 0;
+    uint32_t kb = k & 31;
+    size_t off = (size_t)(k >> 5) * n_pad * 32 + (n >> 3) * 256 + (kb >> 4) * 128 + (n & 7) * 16 + (kb & 15);
+    image[off] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ReLUNorm pieces (inference.c:23-72), thread = one image row
+// ---------------------------------------------------------------------------------------------------
+struct NormCoef { int rounding, cap; uint32_t mult; };
+
+__device__ __forceinline__ NormCoef norm_coef(int row_max_relu) {
+    // shift = bit length of (max >> 7) (inference.c:41-47).  row_max_relu = max(row max, 0): a negative row
+    // maximum zeroes every output whatever the shift, so taking the maximum over relu'd values is equivalent.
+    const uint32_t shift = 32u - (uint32_t)__clz(row_max_relu >> 7);
+    NormCoef c;
+    c.rounding = (int)((1u << shift) >> 1);                 // inference.c:51
+    c.cap = (int)((128u << shift) - 1u);                    // (cap >> shift) == 127: the clip of inference.c:60-64
+    c.mult = 1u << (24u - shift);                           // u * mult puts (u >> shift) into byte 3
+    return c;
+}
+// four int32 accumulators -> four int8 (0..127) packed little-endian.  1 VIADDMNMX.RELU + 1 IMAD per element,
+// 3 PRMT per four.
+__device__ __forceinline__ uint32_t norm_pack4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, const NormCoef &c) {
+    uint32_t z0, z1, z2, z3;
+    // mul.lo via asm so the power-of-two multiply stays an IMAD (FMA pipe) instead of a shift on the ALU pipe
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(z0) : "r"((uint32_t)__viaddmin_s32_relu((int)x0, c.rounding, c.cap)), "r"(c.mult));
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(z1) : "r"((uint32_t)__viaddmin_s32_relu((int)x1, c.rounding, c.cap)), "r"(c.mult));
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(z2) : "r"((uint32_t)__viaddmin_s32_relu((int)x2, c.rounding, c.cap)), "r"(c.mult));
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(z3) : "r"((uint32_t)__viaddmin_s32_relu((int)x3, c.rounding, c.cap)), "r"(c.mult));
+    uint32_t lo = __byte_perm(z0, z1, 0x0073), hi = __byte_perm(z2, z3, 0x0073);
+    return __byte_perm(lo, hi, 0x5410);
+}
+__device__ __forceinline__ int max16(const uint32_t (&v)[16], int m) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) m = __vimax3_s32(m, (int)v[j], (int)v[j + 1]);
+    return m;
+}
+
+// hidden-layer epilogue: D[tmem, n_pad columns] -> A[tmem, n_pad/4 columns]
+__device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, uint32_t n_pad) {
+    if (n_pad <= 64) {
+        // one pass: the whole row (<= 64 accumulators) stays in registers
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if ((uint32_t)c * 16 < n_pad) tmem_ld_x16(d_addr + c * 16, v[c]);
+        tmem_ld_wait();
+        int m = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if ((uint32_t)c * 16 < n_pad) m = max16(v[c], m);
+        const NormCoef k = norm_coef(m);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if ((uint32_t)c * 16 < n_pad) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) w[q] = norm_pack4(v[c][4 * q], v[c][4 * q + 1], v[c][4 * q + 2], v[c][4 * q + 3], k);
+                tmem_st_x4(a_addr + c * 4, w);
+            }
+    } else {
+        // two passes over TMEM (wide layers, e.g. Binary-160): max first, then requantise
+        int m = 0;
+        for (uint32_t c = 0; c < n_pad; c += 16) {
+            uint32_t v[16];
+            tmem_ld_x16(d_addr + c, v);
+            tmem_ld_wait();
+            m = max16(v, m);
+        }
+        const NormCoef k = norm_coef(m);
+        for (uint32_t c = 0; c < n_pad; c += 16) {
+            uint32_t v[16], w[4];
+            tmem_ld_x16(d_addr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; q++) w[q] = norm_pack4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], k);
+            tmem_st_x4(a_addr + (c >> 2), w);
+        }
+    }
+    tmem_st_wait();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMaxWG * 128 + 32, 1)
+fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_mma[kMaxWG];
+    __shared__ uint32_t tmem_base_s;
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t n_wg = P.n_wg, n_st = P.n_stages;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    // ---------------- one-time setup
+    if (tid == 0) {
+        for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (uint32_t g = 0; g < n_wg; g++) mbar_init(&bar_mma[g], 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_in);
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    {   // weight image -> smem (same bytes for every CTA; L2-resident after the first wave)
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.w_image);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem + P.off_w);
+        for (uint32_t i = tid; i < P.w_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
+    const uint32_t my_tiles = tile0 < P.n_tiles ? (P.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+
+    if (warp == n_wg * 4) {
+        // ======================= TMA producer =======================
+        if (elect_one()) {
+            const uint64_t policy = policy_evict_first();   // images are read exactly once
+            for (uint32_t i = 0; i < my_tiles; i++) {
+                const uint32_t s = i % n_st, ph = (i / n_st) & 1;
+                mbar_wait(&bar_empty[s], ph ^ 1, P.err, 1);
+                mbar_arrive_expect_tx(&bar_full[s], P.stage_bytes);
+                const int32_t row = (int32_t)((tile0 + i * tile_step) * kTileM);
+                for (uint32_t a = 0; a < P.in_atoms; a++)
+                    tma_load_2d_hint(smem + s * P.stage_bytes + a * 16384, &tmap_in, (int32_t)(a * 128), row, &bar_full[s], policy);
+            }
+        }
+    } else if (warp < n_wg * 4) {
+        // ======================= compute warpgroups =======================
+        const uint32_t g = warp >> 2, wg_tid = tid & 127, quarter = warp & 3;
+        const uint32_t row_in_tile = quarter * 32 + lane;
+        const uint32_t lane_sel = (quarter * 32) << 16;
+        const uint32_t d_tmem = tmem_base + g * P.tmem_wg_cols;           // accumulator columns of this warpgroup
+        const uint32_t a_tmem = d_tmem + P.tmem_a_off;                    // int8 activations (next layer's A)
+        const uint32_t w_base = smem_base + P.off_w;
+        int32_t *stage_out = reinterpret_cast<int32_t *>(smem + P.off_out + g * P.out_stage_bytes);
+        uint32_t mma_phase = 0;
+        bool store_pending = false;
+
+        for (uint32_t i = g; i < my_tiles; i += n_wg) {
+            const uint32_t s = i % n_st, ph = (i / n_st) & 1;
+            const uint32_t tile = tile0 + i * tile_step;
+            // ---- layer 1: A = TMA tile in smem (SW128 K-major), B = weight tiles
+            if (wg_tid == 0) {
+                mbar_wait(&bar_full[s], ph, P.err, 2);
+                tc_fence_after();
+                const uint32_t a_base = smem_base + s * P.stage_bytes;
+                uint32_t acc = 0;
+                for (uint32_t pl = 0; pl < P.planes[0]; pl++)
+                    for (uint32_t k = 0; k < P.k_steps[0]; k++) {
+                        const uint64_t ad = make_smem_desc(a_base + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, UMMA_LAYOUT_SW128);
+                        const uint64_t bd = make_smem_desc(w_base + P.b_off[0] + (pl * P.k_steps[0] + k) * P.n_pad[0] * 32, 128, 256, UMMA_LAYOUT_NONE);
+                        umma_i8_ss(d_tmem, ad, bd, P.idesc[0], acc);
+                        acc = 1;
+                    }
+                umma_commit(&bar_empty[s]);   // the image tile can be overwritten once these MMAs have read it
+                umma_commit(&bar_mma[g]);
+            }
+            __syncwarp();
+            mbar_wait(&bar_mma[g], mma_phase, P.err, 3);
+            mma_phase ^= 1;
+            tc_fence_after();
+
+            // ---- hidden layers: ReLUNorm in TMEM, then the next MMA with A from TMEM
+            for (int l = 1; l < P.n_layers; l++) {
+                relunorm_tmem(d_tmem + lane_sel, a_tmem + lane_sel, P.n_pad[l - 1]);
+                tc_fence_before();
+                named_bar_sync(1 + g, 128);
+                if (wg_tid == 0) {
+                    tc_fence_after();
+                    uint32_t acc = 0;
+                    for (uint32_t pl = 0; pl < P.planes[l]; pl++)
+                        for (uint32_t k = 0; k < P.k_steps[l]; k++) {
+                            const uint64_t bd = make_smem_desc(w_base + P.b_off[l] + (pl * P.k_steps[l] + k) * P.n_pad[l] * 32, 128, 256, UMMA_LAYOUT_NONE);
+                            umma_i8_ts(d_tmem, a_tmem + k * 8, bd, P.idesc[l], acc);
+                            acc = 1;
+                        }
+                    umma_commit(&bar_mma[g]);
+                }
+                __syncwarp();
+                mbar_wait(&bar_mma[g], mma_phase, P.err, 4);
+                mma_phase ^= 1;
+                tc_fence_after();
+            }
+
+            // ---- logits + label (dll.c:115-116: the last ReLUNorm's argmax is what Inference() returns)
+            const size_t img = (size_t)tile * kTileM + row_in_tile;
+            const uint32_t rows_valid = (uint32_t)min((size_t)kTileM, P.n - (size_t)tile * kTileM);
+            const bool full_tile = rows_valid == kTileM;
+            if (store_pending) {   // the previous bulk store must have finished reading the staging buffer
+                if (wg_tid == 0) bulk_wait_read<0>();
+                named_bar_sync(1 + g, 128);
+                store_pending = false;
+            }
+            int best = -INT32_MAX;
+            uint32_t pos = 255;
+            for (uint32_t c = 0; c < P.n_classes; c += 16) {
+                uint32_t v[16];
+                tmem_ld_x16(d_tmem + lane_sel + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (c + j < P.n_classes) {
+                        const int x = (int)v[j];
+                        if (x > best) { best = x; pos = c + j; }   // strict '>' keeps the first maximum (inference.c:33)
+                        if (full_tile) stage_out[row_in_tile * P.n_classes + c + j] = x;
+                        else if (img < P.n) P.logits[img * P.n_classes + c + j] = x;
+                    }
+                }
+            }
+            if (P.labels && img < P.n) P.labels[img] = pos;
+            tc_fence_before();
+            if (full_tile) {
+                fence_proxy_async_smem();
+                named_bar_sync(1 + g, 128);
+                if (wg_tid == 0) {
+                    bulk_store_1d(P.logits + (size_t)tile * kTileM * P.n_classes, stage_out, P.out_stage_bytes);
+                    bulk_commit();
+                }
+                store_pending = true;
+            } else {
+                named_bar_sync(1 + g, 128);   // TMEM reads done before the next tile's MMA overwrites D
+            }
+        }
+        if (store_pending && wg_tid == 0) bulk_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32_t in_bytes, int device, int sm_count,
+                                  char *err, size_t err_len) {
+    auto fail = [&](const char *msg) -> FcChainPlan * { if (err) snprintf(err, err_len, "%s", msg); return nullptr; };
+    if (n_layers < 1 || n_layers > kMaxFcLayers) return fail("fused path: 1..8 FC layers");
+    if (in_bytes % 16 || in_bytes == 0 || in_bytes > 1024) return fail("fused path: input row must be a multiple of 16 bytes, <= 1024");
+    if (!get_encode_fn()) return fail("cuTensorMapEncodeTiled not available");
+    auto *plan = new FcChainPlan();
+    ChainParams &p = plan->p;
+    p.n_layers = n_layers;
+    p.in_atoms = (in_bytes + 127) / 128;   // weights past the real input width multiply zero activations: dropped
+    p.stage_bytes = p.in_atoms * 16384;
+    uint32_t w_off = 0, d_cols = 0, a_cols = 0;
+    for (int l = 0; l < n_layers; l++) {
+        const FcLayerDev &L = layers[l];
+        if (L.n_pad > 256) { delete plan; return fail("fused path: layer wider than 256 outputs"); }
+        p.n_pad[l] = L.n_pad;
+        p.n_real[l] = L.n_out;
+        p.k_steps[l] = l == 0 ? p.in_atoms * 4 : L.k_pad / 32;
+        p.planes[l] = L.dense_b ? 2 : 1;
+        p.b_off[l] = w_off;
+        p.idesc[l] = make_idesc_i8(128, L.n_pad);
+        w_off += p.planes[l] * p.k_steps[l] * L.n_pad * 32;
+        d_cols = std::max(d_cols, L.n_pad);
+        if (l > 0) a_cols = std::max(a_cols, std::max(L.k_pad, layers[l - 1].n_pad) / 4);
+    }
+    p.w_bytes = w_off;
+    p.n_classes = layers[n_layers - 1].n_out;
+    p.tmem_a_off = round_up(d_cols, 32);
+    p.tmem_wg_cols = p.tmem_a_off + round_up(std::max(a_cols, 1u), 32);
+    if (p.tmem_wg_cols > 512) { delete plan; return fail("fused path: model does not fit the 512 TMEM columns"); }
+    p.n_wg = std::min<uint32_t>(kMaxWG, 512 / p.tmem_wg_cols);
+    p.out_stage_bytes = round_up(kTileM * p.n_classes * 4, 128);
+    const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*static*/;
+    p.off_w = 0;  // set below: stages first (1024-aligned), then weights, then staging
+    uint32_t fixed = round_up(p.w_bytes, 128) + p.n_wg * p.out_stage_bytes;
+    if (fixed + 2 * p.stage_bytes > smem_limit) { delete plan; return fail("fused path: weights do not fit in shared memory"); }
+    p.n_stages = std::min<uint32_t>(kMaxStages, (smem_limit - fixed) / p.stage_bytes);
+    p.n_stages = std::min<uint32_t>(p.n_stages, 6);
+    p.off_w = p.n_stages * p.stage_bytes;
+    p.off_out = p.off_w + round_up(p.w_bytes, 128);
+    plan->smem_bytes = (size_t)p.off_out + p.n_wg * p.out_stage_bytes + 1024;
+    plan->threads = p.n_wg * 128 + 32;
+    plan->in_bytes = in_bytes;
+    plan->sm_count = sm_count;
+    plan->device = device;
+
+    // weight image
+    if (cudaMalloc(&plan->d_w_image, p.w_bytes) != cudaSuccess || cudaMalloc(&plan->d_err, sizeof(int)) != cudaSuccess) {
+        fc_chain_plan_destroy(plan);
+        return fail("cudaMalloc failed (weight image)");
+    }
+    cudaMemset(plan->d_w_image, 0, p.w_bytes);
+    cudaMemset(plan->d_err, 0, sizeof(int));
+    for (int l = 0; l < n_layers; l++) {
+        const FcLayerDev &L = layers[l];
+        for (uint32_t pl = 0; pl < p.planes[l]; pl++) {
+            size_t total = (size_t)L.n_pad * p.k_steps[l] * 32;
+            k_build_b_image<<<(unsigned)((total + 255) / 256), 256>>>(pl ? L.dense_b : L.dense_a, L.k_pad, L.n_pad, p.k_steps[l],
+                                                                      plan->d_w_image + p.b_off[l] + (size_t)pl * p.k_steps[l] * L.n_pad * 32);
+        }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) { fc_chain_plan_destroy(plan); return fail("weight image kernel failed"); }
+    p.w_image = plan->d_w_image;
+    p.err = plan->d_err;
+    if (cudaFuncSetAttribute(fc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
+        fc_chain_plan_destroy(plan);
+        return fail("cannot opt in to the required dynamic shared memory");
+    }
+    return plan;
+}
+
+void fc_chain_plan_destroy(FcChainPlan *p) {
+    if (!p) return;
+    if (p->d_w_image) cudaFree(p->d_w_image);
+    if (p->d_err) cudaFree(p->d_err);
+    delete p;
+}
+
+int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st) {
+    if (n == 0) return 0;
+    if (n > 0x7fffff00ull) return -2;
+    ChainParams p = plan->p;
+    p.logits = logits;
+    p.labels = labels;
+    p.n = n;
+    p.n_tiles = (uint32_t)((n + kTileM - 1) / kTileM);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    cuuint64_t gdim[2] = {(cuuint64_t)plan->in_bytes, (cuuint64_t)n};
+    cuuint64_t gstride[1] = {(cuuint64_t)plan->in_bytes};
+    cuuint32_t box[2] = {128, (cuuint32_t)kTileM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(in), gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -3;
+    unsigned grid = (unsigned)std::min<uint32_t>(p.n_tiles, (uint32_t)plan->sm_count);
+    fc_chain_kernel<<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace bnm

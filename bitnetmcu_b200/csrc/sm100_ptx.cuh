@@ -39,7 +39,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {
+        if (++spins > (1u << 22)) {
             if (err_flag) atomicExch(err_flag, code);
             __threadfence_system();
             asm volatile("trap;");

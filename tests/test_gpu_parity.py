@@ -1,0 +1,258 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA paths, called through the C ABI, against the oracle and
+the committed golden vectors made by the unmodified reference.  Integer work: the bar is bit-exact."""
+import ctypes as C
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_model, model_names
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib(built):
+    from bitnetmcu_b200 import _lib
+    l = _lib.load()
+    assert l.bnm_device_count() > 0, "no CUDA device"
+    return l
+
+
+def _engine(name, path, nf4=False):
+    from bitnetmcu_b200.engine import Engine
+    return Engine(load_model(name), device=0, path=path, nf4_extension=nf4)
+
+
+def _paths(name):
+    from bitnetmcu_b200 import _lib
+    return [_lib.PATH_LAYERS, _lib.PATH_TCGEN05]
+
+
+def _rand_images(n, seed=0):
+    rng = np.random.default_rng(seed)
+    imgs = rng.integers(-128, 128, size=(n, 256)).astype(np.int8)
+    k = min(n, 64)
+    imgs[:k] = np.clip(imgs[:k], -20, 127)        # MNIST-like: background ~ -20, strokes to 127
+    if n > 200:
+        imgs[64:80] = -128
+        imgs[80:96] = 127
+        imgs[96:112] = 0
+        imgs[112:128, ::2] = 0
+    return imgs
+
+
+@pytest.mark.parametrize("path", ["layers", "tcgen05"])
+@pytest.mark.parametrize("name", model_names())
+def test_model_matches_golden_and_oracle(lib, oracle, golden, digits, name, path):
+    from bitnetmcu_b200 import _lib
+    e = _engine(name, _lib.PATH_LAYERS if path == "layers" else _lib.PATH_TCGEN05)
+    assert e.active_path == (_lib.PATH_LAYERS if path == "layers" else _lib.PATH_TCGEN05)
+    imgs, _ = digits
+    lo, la = e.infer(imgs)
+    assert np.array_equal(lo, golden[name + "/digits_logits"]), "digits logits differ from the reference"
+    assert np.array_equal(la, golden[name + "/digits_labels"])
+    xs = oracle.xorshift_images(256)
+    lo, la = e.infer(xs)
+    assert np.array_equal(lo, golden[name + "/xs_logits"])
+    assert np.array_equal(la, golden[name + "/xs_labels"])
+    # ragged random batch (not a multiple of the 128-image tile), full compare with the oracle
+    n = 5000 + 37
+    r = _rand_images(n, seed=len(name))
+    lo, la = e.infer(r)
+    oo, ol = oracle.infer(load_model(name), r)
+    assert np.array_equal(lo, oo), f"{np.argwhere(lo != oo)[:5]}"
+    assert np.array_equal(la, ol)
+    e.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 255, 257, 1000])
+def test_edge_batch_sizes(lib, oracle, n):
+    from bitnetmcu_b200 import _lib
+    for name in ("fc", "cnn_48"):
+        m = load_model(name)
+        for path in (_lib.PATH_LAYERS, _lib.PATH_TCGEN05):
+            e = _engine(name, path)
+            imgs = _rand_images(n, seed=n)
+            lo, la = e.infer(imgs)
+            assert lo.shape == (n, m.n_classes)
+            if n:
+                oo, ol = oracle.infer(m, imgs)
+                assert np.array_equal(lo, oo) and np.array_equal(la, ol)
+            e.close()
+
+
+def test_survey_kat_on_gpu(lib, oracle):
+    """CRC-32 of the first 1000x10 logits of the xorshift stream = fc621bad; label sums."""
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    e = _engine("fc", 0)
+    xs = oracle.xorshift_images(400000)
+    lo, la = e.infer(xs)
+    assert "%08x" % zlib.crc32(lo[:1000].astype("<i4").tobytes()) == kat["fc_xs_crc32_first1000"]
+    assert int(la[:1000].sum()) == kat["fc_xs_sum_labels_1000"]
+    assert int(la.sum()) == kat["fc_xs_sum_labels_400000"]
+    e.close()
+    e = _engine("cnn", 0)
+    _, la = e.infer(xs[:40000])
+    assert int(la.sum()) == kat["cnn_xs_sum_labels_40000"]
+    e.close()
+
+
+def test_nf4_extension(lib, oracle):
+    """id 36 decodes to zeros like the reference (inference.c:202) unless the documented LUT extension is on."""
+    from bitnetmcu_b200 import _lib
+    m = load_model("rand_nf4_64")
+    imgs = _rand_images(777)
+    for path in (_lib.PATH_LAYERS, _lib.PATH_TCGEN05):
+        e = _engine("rand_nf4_64", path)
+        lo, _ = e.infer(imgs)
+        assert not lo.any()
+        e.set_option(_lib.OPT_NF4_EXTENSION, 1)
+        lo, la = e.infer(imgs)
+        oo, ol = oracle.infer(m, imgs, nf4_extension=True)
+        assert oo.any() and np.array_equal(lo, oo) and np.array_equal(la, ol)
+        e.close()
+
+
+@pytest.mark.parametrize("name", ["fc", "binary160", "cnn"])
+def test_full_size_batch_properties(lib, oracle, name):
+    """BASELINE.json sizes (2^20 images): full compare with the oracle where it is quick, plus size-independent
+    properties: shard invariance (batch == concat of shards) and permutation equivariance."""
+    from bitnetmcu_b200 import _lib
+    m = load_model(name)
+    n = 1 << 20
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(-128, 128, size=(n, 256), dtype=np.int8)
+    e = _engine(name, 0)
+    lo, la = e.infer(imgs)
+    # shards of uneven size reproduce the same rows
+    cut = 333333
+    l1, a1 = e.infer(imgs[:cut])
+    l2, a2 = e.infer(imgs[cut:])
+    assert np.array_equal(lo, np.concatenate([l1, l2])) and np.array_equal(la, np.concatenate([a1, a2]))
+    # permutation equivariance on a slice
+    perm = rng.permutation(1 << 16)
+    lp, _ = e.infer(imgs[: 1 << 16][perm])
+    assert np.array_equal(lp, lo[: 1 << 16][perm])
+    # checksum of checksums against the oracle on the full batch (FC) or a 1/8 sample (CNN is slower on CPU)
+    ns = n if m.model_class == 0 else n // 8
+    oo, ol = oracle.infer(m, imgs[:ns])
+    assert zlib.crc32(lo[:ns].tobytes()) == zlib.crc32(oo.tobytes())
+    assert np.array_equal(la[:ns], ol)
+    e.close()
+
+
+def test_host_pipeline_chunks(lib, oracle):
+    from bitnetmcu_b200 import _lib
+    m = load_model("fc")
+    imgs = _rand_images(10000, seed=3)
+    oo, ol = oracle.infer(m, imgs)
+    for chunk in (128, 1024, 4096):
+        e = _engine("fc", 0)
+        e.set_option(_lib.OPT_CHUNK_IMAGES, chunk)
+        lo, la = e.infer(imgs)
+        assert np.array_equal(lo, oo) and np.array_equal(la, ol)
+        lo2, none = e.infer(imgs, want_labels=False)
+        assert none is None and np.array_equal(lo2, oo)
+        e.close()
+
+
+def test_device_api_torch(lib, oracle):
+    import torch
+    m = load_model("fc")
+    imgs = _rand_images(3000, seed=4)
+    oo, ol = oracle.infer(m, imgs)
+    e = _engine("fc", 0)
+    d_img = torch.from_numpy(imgs).cuda()
+    d_log = torch.empty((3000, 10), dtype=torch.int32, device="cuda")
+    d_lab = torch.empty(3000, dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        e.infer_device(d_img, d_log, d_lab)
+    s.synchronize()
+    assert np.array_equal(d_log.cpu().numpy(), oo) and np.array_equal(d_lab.cpu().numpy().astype(np.uint32), ol)
+    assert e.launch_count(3000) == 1
+    e.close()
+
+
+# ---- the four kernels one by one --------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("enc", [1, 2, 4, 12, 16, 20, 36, 64, 3])
+def test_processfclayer_batch(lib, oracle, enc):
+    from bitnetmcu_b200 import engine as E
+    rng = np.random.default_rng(enc)
+    for n_in, n_out in [(256, 64), (64, 10), (160, 160), (320, 7), (32, 1)]:
+        if enc == 64:
+            n_in = (n_in + 9) // 10 * 10
+            w = rng.integers(0, 65536, size=n_out * n_in // 10, dtype=np.uint32).astype(np.uint16)
+        else:
+            w = rng.integers(0, 2 ** 32, size=n_out * n_in // 4 + 4, dtype=np.uint64).astype(np.uint32)
+        act = rng.integers(-128, 128, size=(300, n_in)).astype(np.int8)
+        got = E.processfclayer(act, w, enc, n_in, n_out)
+        want = np.stack([oracle.fclayer(act[i], w, enc, n_in, n_out) for i in range(act.shape[0])])
+        assert np.array_equal(got, want), (enc, n_in, n_out)
+
+
+def test_relunorm_batch(lib, oracle):
+    from bitnetmcu_b200 import engine as E
+    cases = [([127, 128, 255, 256, -3], [32, 32, 64, 64, 0], 3), ([255, 254, 253, 127, 1], [127, 127, 127, 64, 1], 0),
+             ([1000, 509, 510, -1, 1], [125, 64, 64, 0, 0], 0), ([-5, -1, -7], [0, 0, 0], 1)]
+    for x, want, pos in cases:
+        out, p = E.relunorm(np.array(x, dtype=np.int32))
+        assert out[0].tolist() == want and int(p[0]) == pos
+    out, p = E.relunorm(np.array([5, 9, 9, 2], dtype=np.int32))
+    assert int(p[0]) == 1
+    rng = np.random.default_rng(1)
+    for n_in in (1, 10, 33, 64, 160, 256, 1000):
+        for scale in (1, 100, 20000, 500000, 4000000, 2 ** 30):
+            x = rng.integers(-scale, scale + 1, size=(200, n_in)).astype(np.int32)
+            x[::7] = -np.abs(x[::7]) - 1
+            x[5, n_in // 2] = scale
+            out, p = E.relunorm(x)
+            for i in range(0, 200, 3):
+                o, q = oracle.relunorm(x[i])
+                assert q == int(p[i]) and np.array_equal(o, out[i])
+
+
+def test_conv_pool_batch(lib, oracle):
+    from bitnetmcu_b200 import engine as E
+    rng = np.random.default_rng(2)
+    for xy in (16, 14, 6, 4, 3):
+        act = rng.integers(-20000, 20000, size=(50, xy * xy)).astype(np.int32)
+        w = rng.integers(-128, 128, size=(7, 9)).astype(np.int8)
+        got = E.conv33relu(act, w, xy, 4)
+        for i in range(50):
+            assert np.array_equal(got[i], oracle.conv33relu(act[i], w[i % 7], xy, 4))
+        if xy % 2 == 0:
+            gp = E.maxpool22(act, xy)
+            for i in range(50):
+                assert np.array_equal(gp[i], oracle.maxpool22(act[i], xy))
+
+
+def test_reference_named_symbols(lib, oracle):
+    """The drop-in symbols keep the reference signatures (BitNetMCU_inference.h:15-60), host pointers, one item."""
+    rng = np.random.default_rng(3)
+    m = load_model("fc")
+    L = m.layers[0]
+    act = rng.integers(-128, 128, size=256).astype(np.int8)
+    out = np.zeros(64, dtype=np.int32)
+    w = np.ascontiguousarray(L.weights)
+    lib.processfclayer(C.c_void_p(act.ctypes.data), C.c_void_p(w.ctypes.data), L.bitperweight, 256, 64, C.c_void_p(out.ctypes.data))
+    assert np.array_equal(out, oracle.fclayer(act, w, L.bitperweight, 256, 64))
+    inp = out.copy()
+    o8 = np.zeros(64, dtype=np.int8)
+    pos = lib.ReLUNorm(C.c_void_p(inp.ctypes.data), C.c_void_p(o8.ctypes.data), 64)
+    want, wpos = oracle.relunorm(out)
+    assert pos == wpos and np.array_equal(o8, want)
+    assert lib.ReLUNorm(C.c_void_p(inp.ctypes.data), C.c_void_p(o8.ctypes.data), 0) == 255
+    # in-place conv + pool with the returned end pointers (dll.c:71-76)
+    buf = rng.integers(-128, 128, size=256).astype(np.int32)
+    w9 = rng.integers(-128, 128, size=9).astype(np.int8)
+    want = oracle.conv33relu(buf, w9, 16, 4)
+    end = lib.processconv33ReLU(C.c_void_p(buf.ctypes.data), C.c_void_p(w9.ctypes.data), 16, 4, C.c_void_p(buf.ctypes.data))
+    assert end == buf.ctypes.data + 196 * 4 and np.array_equal(buf[:196], want)
+    wantp = oracle.maxpool22(buf[:196], 14)
+    end = lib.processmaxpool22(C.c_void_p(buf.ctypes.data), 14, C.c_void_p(buf.ctypes.data))
+    assert end == buf.ctypes.data + 49 * 4 and np.array_equal(buf[:49], wantp)
