@@ -157,20 +157,21 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxWG * 128 + 32, 1)
+__global__ void __launch_bounds__(kMaxWG * 128, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_mma[kMaxWG];
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_mma[kMaxWG];
     __shared__ uint32_t tmem_base_s;
 
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
     const uint32_t n_wg = P.n_wg, n_st = P.n_stages;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
     // ---------------- one-time setup
     if (tid == 0) {
-        for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (uint32_t s = 0; s < n_st; s++) mbar_init(&bar_full[s], 1);
         for (uint32_t g = 0; g < n_wg; g++) mbar_init(&bar_mma[g], 1);
         fence_mbar_init();
         tma_prefetch_desc(&tmap_in);
@@ -190,20 +191,21 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
     const uint32_t my_tiles = tile0 < P.n_tiles ? (P.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
 
-    if (warp == n_wg * 4) {
-        // ======================= TMA producer =======================
-        if (elect_one()) {
-            const uint64_t policy = policy_evict_first();   // images are read exactly once
-            for (uint32_t i = 0; i < my_tiles; i++) {
-                const uint32_t s = i % n_st, ph = (i / n_st) & 1;
-                mbar_wait(&bar_empty[s], ph ^ 1, P.err, 1);
-                mbar_arrive_expect_tx(&bar_full[s], P.stage_bytes);
-                const int32_t row = (int32_t)((tile0 + i * tile_step) * kTileM);
-                for (uint32_t a = 0; a < P.in_atoms; a++)
-                    tma_load_2d_hint(smem + s * P.stage_bytes + a * 16384, &tmap_in, (int32_t)(a * 128), row, &bar_full[s], policy);
-            }
-        }
-    } else if (warp < n_wg * 4) {
+    // image tile i of this CTA lives in ring stage i % n_st and is consumed by warpgroup i % n_wg.  The first
+    // n_st loads are issued here; afterwards the warpgroup that has just finished reading a stage (its layer-1
+    // MMAs completed) immediately refills it with tile i + n_st -- no dedicated producer warp, no "empty" barriers.
+    const uint64_t l2_policy = policy_evict_first();   // images are read exactly once
+    auto issue_tile_load = [&](uint32_t i) {
+        const uint32_t s = i % n_st;
+        mbar_arrive_expect_tx(&bar_full[s], P.stage_bytes);
+        const int32_t row = (int32_t)((tile0 + i * tile_step) * kTileM);
+        for (uint32_t a = 0; a < P.in_atoms; a++)
+            tma_load_2d_hint(smem + s * P.stage_bytes + a * 16384, &tmap_in, (int32_t)(a * 128), row, &bar_full[s], l2_policy);
+    };
+    if (tid == 0)
+        for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
+
+    if (warp < n_wg * 4) {
         // ======================= compute warpgroups =======================
         const uint32_t g = warp >> 2, wg_tid = tid & 127, quarter = warp & 3;
         const uint32_t row_in_tile = quarter * 32 + lane;
@@ -218,42 +220,47 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         for (uint32_t i = g; i < my_tiles; i += n_wg) {
             const uint32_t s = i % n_st, ph = (i / n_st) & 1;
             const uint32_t tile = tile0 + i * tile_step;
-            // ---- layer 1: A = TMA tile in smem (SW128 K-major), B = weight tiles
-            if (wg_tid == 0) {
+            // ---- layer 1: A = TMA tile in smem (SW128 K-major), B = weight tiles.
+            // The whole first warp of the warpgroup runs the issue loop converged, so descriptors live in the
+            // uniform datapath; only the tcgen05 instructions themselves are predicated on one elected lane.
+            if (quarter == 0) {
                 mbar_wait(&bar_full[s], ph, P.err, 2);
                 tc_fence_after();
-                const uint32_t a_base = smem_base + s * P.stage_bytes;
-                uint32_t acc = 0;
+                const uint64_t a0 = make_smem_desc(smem_base + s * P.stage_bytes, 0, 1024, UMMA_LAYOUT_SW128);
+                const uint64_t b0 = make_smem_desc(w_base + P.b_off[0], 128, 256, UMMA_LAYOUT_NONE);
+                const uint32_t b_step = (P.n_pad[0] * 32) >> 4, nk = P.k_steps[0], idesc = P.idesc[0];
+                const bool leader = elect_one();
+                uint32_t bo = 0;
                 for (uint32_t pl = 0; pl < P.planes[0]; pl++)
-                    for (uint32_t k = 0; k < P.k_steps[0]; k++) {
-                        const uint64_t ad = make_smem_desc(a_base + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, UMMA_LAYOUT_SW128);
-                        const uint64_t bd = make_smem_desc(w_base + P.b_off[0] + (pl * P.k_steps[0] + k) * P.n_pad[0] * 32, 128, 256, UMMA_LAYOUT_NONE);
-                        umma_i8_ss(d_tmem, ad, bd, P.idesc[0], acc);
-                        acc = 1;
+                    for (uint32_t k = 0; k < nk; k++, bo += b_step) {
+                        // K advance inside a SW128 atom: +32 B (>>4 = 2); next atom: +16384 B (>>4 = 1024)
+                        const uint64_t ad = a0 + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
+                        if (leader) umma_i8_ss(d_tmem, ad, b0 + bo, idesc, bo != 0);
                     }
-                umma_commit(&bar_empty[s]);   // the image tile can be overwritten once these MMAs have read it
-                umma_commit(&bar_mma[g]);
+                if (leader) umma_commit(&bar_mma[g]);
             }
             __syncwarp();
             mbar_wait(&bar_mma[g], mma_phase, P.err, 3);
             mma_phase ^= 1;
             tc_fence_after();
+            // the layer-1 MMAs have consumed stage s: refill it (second warp of the group, otherwise idle here)
+            if (quarter == 1 && i + n_st < my_tiles && elect_one()) issue_tile_load(i + n_st);
 
             // ---- hidden layers: ReLUNorm in TMEM, then the next MMA with A from TMEM
             for (int l = 1; l < P.n_layers; l++) {
                 relunorm_tmem(d_tmem + lane_sel, a_tmem + lane_sel, P.n_pad[l - 1]);
                 tc_fence_before();
                 named_bar_sync(1 + g, 128);
-                if (wg_tid == 0) {
+                if (quarter == 0) {
                     tc_fence_after();
-                    uint32_t acc = 0;
+                    const uint64_t b0 = make_smem_desc(w_base + P.b_off[l], 128, 256, UMMA_LAYOUT_NONE);
+                    const uint32_t b_step = (P.n_pad[l] * 32) >> 4, nk = P.k_steps[l], idesc = P.idesc[l];
+                    const bool leader = elect_one();
+                    uint32_t bo = 0;
                     for (uint32_t pl = 0; pl < P.planes[l]; pl++)
-                        for (uint32_t k = 0; k < P.k_steps[l]; k++) {
-                            const uint64_t bd = make_smem_desc(w_base + P.b_off[l] + (pl * P.k_steps[l] + k) * P.n_pad[l] * 32, 128, 256, UMMA_LAYOUT_NONE);
-                            umma_i8_ts(d_tmem, a_tmem + k * 8, bd, P.idesc[l], acc);
-                            acc = 1;
-                        }
-                    umma_commit(&bar_mma[g]);
+                        for (uint32_t k = 0; k < nk; k++, bo += b_step)
+                            if (leader) umma_i8_ts(d_tmem, a_tmem + k * 8, b0 + bo, idesc, bo != 0);
+                    if (leader) umma_commit(&bar_mma[g]);
                 }
                 __syncwarp();
                 mbar_wait(&bar_mma[g], mma_phase, P.err, 4);
@@ -368,7 +375,7 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     p.off_w = p.n_stages * p.stage_bytes;
     p.off_out = p.off_w + round_up(p.w_bytes, 128);
     plan->smem_bytes = (size_t)p.off_out + p.n_wg * p.out_stage_bytes + 1024;
-    plan->threads = p.n_wg * 128 + 32;
+    plan->threads = p.n_wg * 128;
     plan->in_bytes = in_bytes;
     plan->sm_count = sm_count;
     plan->device = device;
