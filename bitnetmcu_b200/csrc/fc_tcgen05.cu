@@ -15,6 +15,7 @@
 // +128 does not fit s8 and is carried by a second residual plane accumulated by extra MMAs into the same D.
 // All arithmetic is integer: results are bit-exact with the reference.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -23,7 +24,7 @@
 
 namespace bnm {
 
-constexpr int kMaxWG = 4;
+constexpr int kMaxWG = 6;        // 6 x (64 D + 16 A columns) = 480 of the 512 TMEM columns for the 64-wide models
 constexpr int kMaxStages = 8;
 
 struct ChainParams {
@@ -48,6 +49,7 @@ struct ChainParams {
     uint32_t *labels;
     size_t n;
     int *err;
+    long long *trace;                 // diagnostics: clock64 per phase of CTA 0 / warpgroup 0 (null in production)
 };
 
 struct FcChainPlan {
@@ -111,8 +113,9 @@ __device__ __forceinline__ int max16(const uint32_t (&v)[16], int m) {
 }
 
 // hidden-layer epilogue: D[tmem, n_pad columns] -> A[tmem, n_pad/4 columns]
+template <bool kOnePass>
 __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, uint32_t n_pad) {
-    if (n_pad <= 64) {
+    if (kOnePass && n_pad <= 64) {
         // one pass: the whole row (<= 64 accumulators) stays in registers
         uint32_t v[4][16];
 #pragma unroll
@@ -133,7 +136,8 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
                 tmem_st_x4(a_addr + c * 4, w);
             }
     } else {
-        // two passes over TMEM (wide layers, e.g. Binary-160): max first, then requantise
+        // two passes over TMEM (wide layers such as Binary-160, and the high-occupancy variant where 64
+        // accumulators per thread would not fit the register budget): max first, then requantise
         int m = 0;
         for (uint32_t c = 0; c < n_pad; c += 16) {
             uint32_t v[16];
@@ -157,10 +161,11 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxWG * 128, 1)
+template <int kWG>
+__global__ void __launch_bounds__(kWG * 128, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_mma[kMaxWG];
+    __shared__ __align__(8) uint64_t bar_full[2][kMaxStages], bar_mma[kMaxWG];
     __shared__ uint32_t tmem_base_s;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -171,7 +176,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
     // ---------------- one-time setup
     if (tid == 0) {
-        for (uint32_t s = 0; s < n_st; s++) mbar_init(&bar_full[s], 1);
+        for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[0][s], 1); mbar_init(&bar_full[1][s], 1); }
         for (uint32_t g = 0; g < n_wg; g++) mbar_init(&bar_mma[g], 1);
         fence_mbar_init();
         tma_prefetch_desc(&tmap_in);
@@ -195,12 +200,16 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     // n_st loads are issued here; afterwards the warpgroup that has just finished reading a stage (its layer-1
     // MMAs completed) immediately refills it with tile i + n_st -- no dedicated producer warp, no "empty" barriers.
     const uint64_t l2_policy = policy_evict_first();   // images are read exactly once
+    // Ring round u = i / n_st of stage s signals barrier bar_full[u & 1][s] (phase (u >> 1) & 1): with two barriers
+    // per stage a parity wait stays unambiguous even when a warpgroup runs a whole round ahead of the loads
+    // (n_wg > n_stages) -- "still in the previous phase" would now mean being four rounds ahead, which cannot happen.
     auto issue_tile_load = [&](uint32_t i) {
         const uint32_t s = i % n_st;
-        mbar_arrive_expect_tx(&bar_full[s], P.stage_bytes);
+        uint64_t *bar = &bar_full[(i / n_st) & 1][s];
+        mbar_arrive_expect_tx(bar, P.stage_bytes);
         const int32_t row = (int32_t)((tile0 + i * tile_step) * kTileM);
         for (uint32_t a = 0; a < P.in_atoms; a++)
-            tma_load_2d_hint(smem + s * P.stage_bytes + a * 16384, &tmap_in, (int32_t)(a * 128), row, &bar_full[s], l2_policy);
+            tma_load_2d_hint(smem + s * P.stage_bytes + a * 16384, &tmap_in, (int32_t)(a * 128), row, bar, l2_policy);
     };
     if (tid == 0)
         for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
@@ -217,14 +226,18 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         uint32_t mma_phase = 0;
         bool store_pending = false;
 
+        const bool tracing = P.trace != nullptr && blockIdx.x == 0 && g == 0 && wg_tid == 0;
+        uint32_t trace_n = 0;
+#define BNM_TRACE_POINT() do { if (tracing && trace_n < 1024) P.trace[trace_n++] = clock64(); } while (0)
         for (uint32_t i = g; i < my_tiles; i += n_wg) {
-            const uint32_t s = i % n_st, ph = (i / n_st) & 1;
+            const uint32_t s = i % n_st, ph = (i / (2 * n_st)) & 1;
+            BNM_TRACE_POINT();   // 0: tile start
             const uint32_t tile = tile0 + i * tile_step;
             // ---- layer 1: A = TMA tile in smem (SW128 K-major), B = weight tiles.
             // The whole first warp of the warpgroup runs the issue loop converged, so descriptors live in the
             // uniform datapath; only the tcgen05 instructions themselves are predicated on one elected lane.
             if (quarter == 0) {
-                mbar_wait(&bar_full[s], ph, P.err, 2);
+                mbar_wait(&bar_full[(i / n_st) & 1][s], ph, P.err, 2);
                 tc_fence_after();
                 const uint64_t a0 = make_smem_desc(smem_base + s * P.stage_bytes, 0, 1024, UMMA_LAYOUT_SW128);
                 const uint64_t b0 = make_smem_desc(w_base + P.b_off[0], 128, 256, UMMA_LAYOUT_NONE);
@@ -240,6 +253,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                 if (leader) umma_commit(&bar_mma[g]);
             }
             __syncwarp();
+            BNM_TRACE_POINT();   // 1: image tile landed + layer-1 MMAs issued
             mbar_wait(&bar_mma[g], mma_phase, P.err, 3);
             mma_phase ^= 1;
             tc_fence_after();
@@ -248,9 +262,12 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
             // ---- hidden layers: ReLUNorm in TMEM, then the next MMA with A from TMEM
             for (int l = 1; l < P.n_layers; l++) {
-                relunorm_tmem(d_tmem + lane_sel, a_tmem + lane_sel, P.n_pad[l - 1]);
+                BNM_TRACE_POINT();   // 2+4(l-1): MMAs of layer l complete
+                relunorm_tmem<(kWG <= 4)>(d_tmem + lane_sel, a_tmem + lane_sel, P.n_pad[l - 1]);
                 tc_fence_before();
+                BNM_TRACE_POINT();   // 3+4(l-1): own ReLUNorm done
                 named_bar_sync(1 + g, 128);
+                BNM_TRACE_POINT();   // 4+4(l-1): whole warpgroup done
                 if (quarter == 0) {
                     tc_fence_after();
                     const uint64_t b0 = make_smem_desc(w_base + P.b_off[l], 128, 256, UMMA_LAYOUT_NONE);
@@ -263,11 +280,13 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                     if (leader) umma_commit(&bar_mma[g]);
                 }
                 __syncwarp();
+                BNM_TRACE_POINT();   // 5+4(l-1): next MMAs issued
                 mbar_wait(&bar_mma[g], mma_phase, P.err, 4);
                 mma_phase ^= 1;
                 tc_fence_after();
             }
 
+            BNM_TRACE_POINT();   // last MMAs complete
             // ---- logits + label (dll.c:115-116: the last ReLUNorm's argmax is what Inference() returns)
             const size_t img = (size_t)tile * kTileM + row_in_tile;
             const uint32_t rows_valid = (uint32_t)min((size_t)kTileM, P.n - (size_t)tile * kTileM);
@@ -277,20 +296,29 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                 named_bar_sync(1 + g, 128);
                 store_pending = false;
             }
+            // argmax = first maximum (strict '>' from -INT32_MAX / 255, inference.c:32-37).  Within a 16-column chunk
+            // the scan is a max over keys x*16 + (15-j): equal x -> the smaller j wins.  |x| < 2^27 is guaranteed by the
+            // plan (n_in <= 1024, int8 x int8), so the key cannot overflow.
             int best = -INT32_MAX;
             uint32_t pos = 255;
             for (uint32_t c = 0; c < P.n_classes; c += 16) {
                 uint32_t v[16];
                 tmem_ld_x16(d_tmem + lane_sel + c, v);
                 tmem_ld_wait();
+                int key = INT32_MIN;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    if (c + j < P.n_classes) {
-                        const int x = (int)v[j];
-                        if (x > best) { best = x; pos = c + j; }   // strict '>' keeps the first maximum (inference.c:33)
-                        if (full_tile) stage_out[row_in_tile * P.n_classes + c + j] = x;
-                        else if (img < P.n) P.logits[img * P.n_classes + c + j] = x;
-                    }
+                for (int j = 0; j < 16; j += 2) {
+                    const int k0 = c + j < P.n_classes ? (int)v[j] * 16 + (15 - j) : INT32_MIN;
+                    const int k1 = c + j + 1 < P.n_classes ? (int)v[j + 1] * 16 + (14 - j) : INT32_MIN;
+                    key = __vimax3_s32(key, k0, k1);
+                }
+                const int cx = key >> 4;
+                if (cx > best) { best = cx; pos = c + 15 - (key & 15); }
+                int32_t *dst = full_tile ? stage_out + row_in_tile * P.n_classes + c : P.logits + img * P.n_classes + c;
+                if (full_tile || img < P.n) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (c + j < P.n_classes) dst[j] = (int)v[j];
                 }
             }
             if (P.labels && img < P.n) P.labels[img] = pos;
@@ -306,6 +334,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
             } else {
                 named_bar_sync(1 + g, 128);   // TMEM reads done before the next tile's MMA overwrites D
             }
+            BNM_TRACE_POINT();   // tile end
         }
         if (store_pending && wg_tid == 0) bulk_wait_all<0>();
     }
@@ -362,9 +391,10 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     p.w_bytes = w_off;
     p.n_classes = layers[n_layers - 1].n_out;
     p.tmem_a_off = round_up(d_cols, 32);
-    p.tmem_wg_cols = p.tmem_a_off + round_up(std::max(a_cols, 1u), 32);
+    p.tmem_wg_cols = p.tmem_a_off + round_up(std::max(a_cols, 1u), 16);
     if (p.tmem_wg_cols > 512) { delete plan; return fail("fused path: model does not fit the 512 TMEM columns"); }
     p.n_wg = std::min<uint32_t>(kMaxWG, 512 / p.tmem_wg_cols);
+    if (const char *e = getenv("BNM_WG")) p.n_wg = std::max(1, std::min<int>((int)p.n_wg, atoi(e)));   // tuning knob
     p.out_stage_bytes = round_up(kTileM * p.n_classes * 4, 128);
     const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*static*/;
     p.off_w = 0;  // set below: stages first (1024-aligned), then weights, then staging
@@ -398,7 +428,8 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     if (cudaDeviceSynchronize() != cudaSuccess) { fc_chain_plan_destroy(plan); return fail("weight image kernel failed"); }
     p.w_image = plan->d_w_image;
     p.err = plan->d_err;
-    if (cudaFuncSetAttribute(fc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(fc_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
         return fail("cannot opt in to the required dynamic shared memory");
     }
@@ -431,7 +462,22 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -3;
     unsigned grid = (unsigned)std::min<uint32_t>(p.n_tiles, (uint32_t)plan->sm_count);
-    fc_chain_kernel<<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+    long long *d_trace = nullptr;
+    const char *trace_path = getenv("BNM_TRACE");
+    if (trace_path) { cudaMalloc(&d_trace, 1024 * sizeof(long long)); cudaMemset(d_trace, 0, 1024 * sizeof(long long)); }
+    p.trace = d_trace;
+    if (p.n_wg <= 4) fc_chain_kernel<4><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+    else fc_chain_kernel<6><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+    if (trace_path) {   // diagnostics only: synchronous dump of the phase clocks
+        std::vector<long long> h(1024);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), d_trace, 1024 * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        if (FILE *f = fopen(trace_path, "w")) {
+            for (int i = 0; i < 1024 && h[i]; i++) fprintf(f, "%lld\n", h[i]);
+            fclose(f);
+        }
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
