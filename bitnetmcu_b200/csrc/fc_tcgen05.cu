@@ -24,7 +24,7 @@
 
 namespace bnm {
 
-constexpr int kMaxWG = 6;        // 6 x (64 D + 16 A columns) = 480 of the 512 TMEM columns for the 64-wide models
+constexpr int kMaxWG = 3;        // epilogue warpgroups; with 2 slots each: 6 x (64 D + 16 A) = 480 of the 512 TMEM columns
 constexpr int kMaxStages = 8;
 
 struct ChainParams {
@@ -37,7 +37,7 @@ struct ChainParams {
     uint32_t idesc[kMaxFcLayers];
     uint32_t in_atoms;                // layer-1 A: 128-byte SW128 atoms per row (TMA boxes per tile)
     uint32_t stage_bytes;             // in_atoms * 128 rows * 128 B
-    uint32_t n_stages, n_wg;
+    uint32_t n_stages, n_wg, n_slots;
     uint32_t w_bytes;                 // weight image bytes (multiple of 16)
     uint32_t off_w, off_out;          // smem offsets (from the 1024-aligned base): weights, per-WG logits staging
     uint32_t out_stage_bytes;         // per-WG staging bytes = 128 * n_classes * 4
@@ -107,9 +107,13 @@ __device__ __forceinline__ uint32_t norm_pack4(uint32_t x0, uint32_t x1, uint32_
     return __byte_perm(lo, hi, 0x5410);
 }
 __device__ __forceinline__ int max16(const uint32_t (&v)[16], int m) {
+    int m2 = 0;   // two interleaved chains; every value is compared against 0 anyway (relu'd maximum)
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) m = __vimax3_s32(m, (int)v[j], (int)v[j + 1]);
-    return m;
+    for (int j = 0; j < 16; j += 4) {
+        m = __vimax3_s32(m, (int)v[j], (int)v[j + 1]);
+        m2 = __vimax3_s32(m2, (int)v[j + 2], (int)v[j + 3]);
+    }
+    return max(m, m2);
 }
 
 // hidden-layer epilogue: D[tmem, n_pad columns] -> A[tmem, n_pad/4 columns]
@@ -122,11 +126,11 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
         for (int c = 0; c < 4; c++)
             if ((uint32_t)c * 16 < n_pad) tmem_ld_x16(d_addr + c * 16, v[c]);
         tmem_ld_wait();
-        int m = 0;
+        int mc[4] = {0, 0, 0, 0};   // four independent max chains (ILP), merged at the end
 #pragma unroll
         for (int c = 0; c < 4; c++)
-            if ((uint32_t)c * 16 < n_pad) m = max16(v[c], m);
-        const NormCoef k = norm_coef(m);
+            if ((uint32_t)c * 16 < n_pad) mc[c] = max16(v[c], 0);
+        const NormCoef k = norm_coef(max(__vimax3_s32(mc[0], mc[1], mc[2]), mc[3]));
 #pragma unroll
         for (int c = 0; c < 4; c++)
             if ((uint32_t)c * 16 < n_pad) {
@@ -139,6 +143,7 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
         // two passes over TMEM (wide layers such as Binary-160, and the high-occupancy variant where 64
         // accumulators per thread would not fit the register budget): max first, then requantise
         int m = 0;
+#pragma unroll 1
         for (uint32_t c = 0; c < n_pad; c += 16) {
             uint32_t v[16];
             tmem_ld_x16(d_addr + c, v);
@@ -146,6 +151,7 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
             m = max16(v, m);
         }
         const NormCoef k = norm_coef(m);
+#pragma unroll 1
         for (uint32_t c = 0; c < n_pad; c += 16) {
             uint32_t v[16], w[4];
             tmem_ld_x16(d_addr + c, v);
@@ -160,12 +166,50 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
+//
+// Roles (one CTA per SM, persistent over image tiles):
+//   * n_wg epilogue warpgroups (4 warps = the 4 TMEM lane quarters).  Every warp owns 32 image rows and works
+//     alone: it never synchronises with the other warps of its group.
+//   * n_wg issuer warps, one per warpgroup: they wait for "operand ready", issue the tcgen05.mma batch of the next
+//     layer and commit it to an mbarrier.  tcgen05.mma issue + commit blocks the issuing warp for roughly the MMA
+//     pipeline latency (~450 cycles, tools/umma_tput.cu), so it lives in its own warp, off the epilogue's path.
+//   * every warpgroup runs kSlots tiles at once ("slots", each with its own TMEM accumulator + activation columns):
+//     while the MMAs of slot X are in flight the epilogue warps requantise slot Y, so the integer ALU work of
+//     ReLUNorm -- the real limiter of this kernel -- is never parked behind tensor-pipe latency.
+// Barriers: full[2][stage] (TMA tile landed), mma[g][slot] (MMA batch complete -> epilogue may read D),
+//           ready[g][slot] (4 arrivals: every epilogue warp has written A / finished reading D -> issuer may go on).
 // ---------------------------------------------------------------------------------------------------
-template <int kWG>
-__global__ void __launch_bounds__(kWG * 128, 1)
+constexpr int kMaxSlots = 2;
+
+// layer-1 MMAs: A = image tile in smem (SWIZZLE_128B K-major), B = weight tiles.  Whole warp converged so that all
+// descriptor arithmetic stays in the uniform datapath; only the tcgen05 instructions are predicated on one lane.
+__device__ __forceinline__ void issue_layer1(const ChainParams &P, uint32_t a_stage_addr, uint32_t w_base, uint32_t d_tmem, bool leader) {
+    const uint64_t a0 = make_smem_desc(a_stage_addr, 0, 1024, UMMA_LAYOUT_SW128);
+    const uint64_t b0 = make_smem_desc(w_base + P.b_off[0], 128, 256, UMMA_LAYOUT_NONE);
+    const uint32_t b_step = (P.n_pad[0] * 32) >> 4, nk = P.k_steps[0], idesc = P.idesc[0];
+    uint32_t bo = 0;
+    for (uint32_t pl = 0; pl < P.planes[0]; pl++)
+        for (uint32_t k = 0; k < nk; k++, bo += b_step) {
+            // K advance inside a SW128 atom: +32 B (>>4 = 2); next atom: +16384 B (>>4 = 1024)
+            const uint64_t ad = a0 + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
+            if (leader) umma_i8_ss(d_tmem, ad, b0 + bo, idesc, bo != 0);
+        }
+}
+// layer l > 1: A = int8 activations in TMEM (written by the ReLUNorm epilogue), B = weight tiles
+__device__ __forceinline__ void issue_layer_ts(const ChainParams &P, int l, uint32_t w_base, uint32_t d_tmem, uint32_t a_tmem, bool leader) {
+    const uint64_t b0 = make_smem_desc(w_base + P.b_off[l], 128, 256, UMMA_LAYOUT_NONE);
+    const uint32_t b_step = (P.n_pad[l] * 32) >> 4, nk = P.k_steps[l], idesc = P.idesc[l];
+    uint32_t bo = 0;
+    for (uint32_t pl = 0; pl < P.planes[l]; pl++)
+        for (uint32_t k = 0; k < nk; k++, bo += b_step)
+            if (leader) umma_i8_ts(d_tmem, a_tmem + k * 8, b0 + bo, idesc, bo != 0);
+}
+
+template <int kSlots, bool kTrace>
+__global__ void __launch_bounds__(kMaxWG * 160, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[2][kMaxStages], bar_mma[kMaxWG];
+    __shared__ __align__(8) uint64_t bar_full[2][kMaxStages], bar_mma[kMaxWG][kMaxSlots], bar_ready[kMaxWG][kMaxSlots];
     __shared__ uint32_t tmem_base_s;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -177,7 +221,8 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     // ---------------- one-time setup
     if (tid == 0) {
         for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[0][s], 1); mbar_init(&bar_full[1][s], 1); }
-        for (uint32_t g = 0; g < n_wg; g++) mbar_init(&bar_mma[g], 1);
+        for (uint32_t g = 0; g < n_wg; g++)
+            for (int q = 0; q < kSlots; q++) { mbar_init(&bar_mma[g][q], 1); mbar_init(&bar_ready[g][q], 4); }
         fence_mbar_init();
         tma_prefetch_desc(&tmap_in);
     }
@@ -195,14 +240,15 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
     const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
     const uint32_t my_tiles = tile0 < P.n_tiles ? (P.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+    const uint32_t n_virt = n_wg * kSlots;                 // tiles in flight per CTA
+    const uint32_t n_rounds = (my_tiles + n_virt - 1) / n_virt;
+    const uint32_t w_base = smem_base + P.off_w;
 
-    // image tile i of this CTA lives in ring stage i % n_st and is consumed by warpgroup i % n_wg.  The first
-    // n_st loads are issued here; afterwards the warpgroup that has just finished reading a stage (its layer-1
-    // MMAs completed) immediately refills it with tile i + n_st -- no dedicated producer warp, no "empty" barriers.
+    // Image tile i of this CTA lives in ring stage i % n_st and belongs to slot (i % n_virt).  The first n_st loads are
+    // issued here; afterwards the warp that has just seen the layer-1 MMAs of tile i complete (stage free) refills the
+    // stage with tile i + n_st.  Ring round u = i / n_st signals barrier bar_full[u & 1][s] (phase (u >> 1) & 1): with
+    // two barriers per stage a parity wait stays unambiguous even when a slot runs a whole round ahead of the loads.
     const uint64_t l2_policy = policy_evict_first();   // images are read exactly once
-    // Ring round u = i / n_st of stage s signals barrier bar_full[u & 1][s] (phase (u >> 1) & 1): with two barriers
-    // per stage a parity wait stays unambiguous even when a warpgroup runs a whole round ahead of the loads
-    // (n_wg > n_stages) -- "still in the previous phase" would now mean being four rounds ahead, which cannot happen.
     auto issue_tile_load = [&](uint32_t i) {
         const uint32_t s = i % n_st;
         uint64_t *bar = &bar_full[(i / n_st) & 1][s];
@@ -214,129 +260,112 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     if (tid == 0)
         for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
 
-    if (warp < n_wg * 4) {
-        // ======================= compute warpgroups =======================
-        const uint32_t g = warp >> 2, wg_tid = tid & 127, quarter = warp & 3;
-        const uint32_t row_in_tile = quarter * 32 + lane;
-        const uint32_t lane_sel = (quarter * 32) << 16;
-        const uint32_t d_tmem = tmem_base + g * P.tmem_wg_cols;           // accumulator columns of this warpgroup
-        const uint32_t a_tmem = d_tmem + P.tmem_a_off;                    // int8 activations (next layer's A)
-        const uint32_t w_base = smem_base + P.off_w;
-        int32_t *stage_out = reinterpret_cast<int32_t *>(smem + P.off_out + g * P.out_stage_bytes);
-        uint32_t mma_phase = 0;
-        bool store_pending = false;
-
-        const bool tracing = P.trace != nullptr && blockIdx.x == 0 && g == 0 && wg_tid == 0;
-        uint32_t trace_n = 0;
-#define BNM_TRACE_POINT() do { if (tracing && trace_n < 1024) P.trace[trace_n++] = clock64(); } while (0)
-        for (uint32_t i = g; i < my_tiles; i += n_wg) {
-            const uint32_t s = i % n_st, ph = (i / (2 * n_st)) & 1;
-            BNM_TRACE_POINT();   // 0: tile start
-            const uint32_t tile = tile0 + i * tile_step;
-            // ---- layer 1: A = TMA tile in smem (SW128 K-major), B = weight tiles.
-            // The whole first warp of the warpgroup runs the issue loop converged, so descriptors live in the
-            // uniform datapath; only the tcgen05 instructions themselves are predicated on one elected lane.
-            if (quarter == 0) {
-                mbar_wait(&bar_full[(i / n_st) & 1][s], ph, P.err, 2);
-                tc_fence_after();
-                const uint64_t a0 = make_smem_desc(smem_base + s * P.stage_bytes, 0, 1024, UMMA_LAYOUT_SW128);
-                const uint64_t b0 = make_smem_desc(w_base + P.b_off[0], 128, 256, UMMA_LAYOUT_NONE);
-                const uint32_t b_step = (P.n_pad[0] * 32) >> 4, nk = P.k_steps[0], idesc = P.idesc[0];
-                const bool leader = elect_one();
-                uint32_t bo = 0;
-                for (uint32_t pl = 0; pl < P.planes[0]; pl++)
-                    for (uint32_t k = 0; k < nk; k++, bo += b_step) {
-                        // K advance inside a SW128 atom: +32 B (>>4 = 2); next atom: +16384 B (>>4 = 1024)
-                        const uint64_t ad = a0 + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
-                        if (leader) umma_i8_ss(d_tmem, ad, b0 + bo, idesc, bo != 0);
+    if (warp >= n_wg * 4 && warp < n_wg * 5) {
+        // ======================= MMA issuer warp of warpgroup g =======================
+        const uint32_t g = warp - n_wg * 4;
+        const bool leader = elect_one();
+        uint32_t ready_phase = 0;   // one phase bit per slot
+        for (uint32_t r = 0; r < n_rounds; r++)
+            for (int l = 0; l < P.n_layers; l++)
+#pragma unroll 1
+                for (int q = 0; q < kSlots; q++) {
+                    const uint32_t v = g * kSlots + q, i = r * n_virt + v;
+                    if (i >= my_tiles) continue;
+                    const uint32_t d_tmem = tmem_base + v * P.tmem_wg_cols, a_tmem = d_tmem + P.tmem_a_off;
+                    if (r != 0 || l != 0) {   // previous epilogue step of this slot: A written / D drained by all 4 warps
+                        mbar_wait(&bar_ready[g][q], (ready_phase >> q) & 1, P.err, 4);
+                        ready_phase ^= 1u << q;
                     }
-                if (leader) umma_commit(&bar_mma[g]);
-            }
-            __syncwarp();
-            BNM_TRACE_POINT();   // 1: image tile landed + layer-1 MMAs issued
-            mbar_wait(&bar_mma[g], mma_phase, P.err, 3);
-            mma_phase ^= 1;
-            tc_fence_after();
-            // the layer-1 MMAs have consumed stage s: refill it (second warp of the group, otherwise idle here)
-            if (quarter == 1 && i + n_st < my_tiles && elect_one()) issue_tile_load(i + n_st);
+                    if (l == 0) {
+                        const uint32_t s = i % n_st;
+                        mbar_wait(&bar_full[(i / n_st) & 1][s], (i / (2 * n_st)) & 1, P.err, 2);
+                        tc_fence_after();
+                        issue_layer1(P, smem_base + s * P.stage_bytes, w_base, d_tmem, leader);
+                    } else {
+                        tc_fence_after();
+                        issue_layer_ts(P, l, w_base, d_tmem, a_tmem, leader);
+                    }
+                    if (leader) umma_commit(&bar_mma[g][q]);
+                    __syncwarp();
+                }
+    } else if (warp < n_wg * 4) {
+        // ======================= epilogue warps =======================
+        const uint32_t g = warp >> 2, quarter = warp & 3;
+        const uint32_t lane_sel = (quarter * 32) << 16;
+        const uint32_t warp_stage_bytes = 32 * P.n_classes * 4;
+        uint32_t mma_phase = 0, store_pending = 0;   // one bit per slot (keeps the slot loop rolled: code size / I-cache)
+        const bool tracing = kTrace && P.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
+        uint32_t trace_n = 0;
+#define BNM_TRACE_POINT() do { if (kTrace && tracing && trace_n < 1024) P.trace[trace_n++] = clock64(); } while (0)
 
-            // ---- hidden layers: ReLUNorm in TMEM, then the next MMA with A from TMEM
-            for (int l = 1; l < P.n_layers; l++) {
-                BNM_TRACE_POINT();   // 2+4(l-1): MMAs of layer l complete
-                relunorm_tmem<(kWG <= 4)>(d_tmem + lane_sel, a_tmem + lane_sel, P.n_pad[l - 1]);
-                tc_fence_before();
-                BNM_TRACE_POINT();   // 3+4(l-1): own ReLUNorm done
-                named_bar_sync(1 + g, 128);
-                BNM_TRACE_POINT();   // 4+4(l-1): whole warpgroup done
-                if (quarter == 0) {
+        for (uint32_t r = 0; r < n_rounds; r++)
+            for (int l = 0; l < P.n_layers; l++)
+#pragma unroll 1
+                for (int q = 0; q < kSlots; q++) {
+                    const uint32_t v = g * kSlots + q, i = r * n_virt + v;
+                    if (i >= my_tiles) continue;
+                    const uint32_t d_tmem = tmem_base + v * P.tmem_wg_cols + lane_sel, a_tmem = d_tmem + P.tmem_a_off;
+                    BNM_TRACE_POINT();   // step start
+                    mbar_wait(&bar_mma[g][q], (mma_phase >> q) & 1, P.err, 3);
+                    mma_phase ^= 1u << q;
                     tc_fence_after();
-                    const uint64_t b0 = make_smem_desc(w_base + P.b_off[l], 128, 256, UMMA_LAYOUT_NONE);
-                    const uint32_t b_step = (P.n_pad[l] * 32) >> 4, nk = P.k_steps[l], idesc = P.idesc[l];
-                    const bool leader = elect_one();
-                    uint32_t bo = 0;
-                    for (uint32_t pl = 0; pl < P.planes[l]; pl++)
-                        for (uint32_t k = 0; k < nk; k++, bo += b_step)
-                            if (leader) umma_i8_ts(d_tmem, a_tmem + k * 8, b0 + bo, idesc, bo != 0);
-                    if (leader) umma_commit(&bar_mma[g]);
-                }
-                __syncwarp();
-                BNM_TRACE_POINT();   // 5+4(l-1): next MMAs issued
-                mbar_wait(&bar_mma[g], mma_phase, P.err, 4);
-                mma_phase ^= 1;
-                tc_fence_after();
-            }
-
-            BNM_TRACE_POINT();   // last MMAs complete
-            // ---- logits + label (dll.c:115-116: the last ReLUNorm's argmax is what Inference() returns)
-            const size_t img = (size_t)tile * kTileM + row_in_tile;
-            const uint32_t rows_valid = (uint32_t)min((size_t)kTileM, P.n - (size_t)tile * kTileM);
-            const bool full_tile = rows_valid == kTileM;
-            if (store_pending) {   // the previous bulk store must have finished reading the staging buffer
-                if (wg_tid == 0) bulk_wait_read<0>();
-                named_bar_sync(1 + g, 128);
-                store_pending = false;
-            }
-            // argmax = first maximum (strict '>' from -INT32_MAX / 255, inference.c:32-37).  Within a 16-column chunk
-            // the scan is a max over keys x*16 + (15-j): equal x -> the smaller j wins.  |x| < 2^27 is guaranteed by the
-            // plan (n_in <= 1024, int8 x int8), so the key cannot overflow.
-            int best = -INT32_MAX;
-            uint32_t pos = 255;
-            for (uint32_t c = 0; c < P.n_classes; c += 16) {
-                uint32_t v[16];
-                tmem_ld_x16(d_tmem + lane_sel + c, v);
-                tmem_ld_wait();
-                int key = INT32_MIN;
+                    BNM_TRACE_POINT();   // MMAs of layer l+1 complete
+                    if (l == 0 && quarter == 1 && i + n_st < my_tiles && elect_one()) issue_tile_load(i + n_st);   // stage is free
+                    if (l + 1 < P.n_layers) {
+                        relunorm_tmem<true>(d_tmem, a_tmem, P.n_pad[l]);
+                    } else {
+                        // ---- logits + label (dll.c:115-116: the last ReLUNorm's argmax is what Inference() returns)
+                        const uint32_t tile = tile0 + i * tile_step;
+                        const size_t img = (size_t)tile * kTileM + quarter * 32 + lane;
+                        const bool full_tile = (size_t)(tile + 1) * kTileM <= P.n;
+                        int32_t *stage_out = reinterpret_cast<int32_t *>(smem + P.off_out + (v * 4 + quarter) * warp_stage_bytes);
+                        if ((store_pending >> q) & 1) {   // the previous bulk store of this slot must have finished reading the staging rows
+                            if (lane == 0) bulk_wait_read<kSlots - 1>();
+                            __syncwarp();
+                        }
+                        // argmax = first maximum (strict '>' from -INT32_MAX / 255, inference.c:32-37).  Within a 16-column
+                        // chunk the scan is a max over keys x*16 + (15-j): equal x -> the smaller j wins.  |x| < 2^27 is
+                        // guaranteed by the plan (n_in <= 1024, int8 x int8), so the key cannot overflow.
+                        int best = -INT32_MAX;
+                        uint32_t pos = 255;
+                        for (uint32_t c = 0; c < P.n_classes; c += 16) {
+                            uint32_t x[16];
+                            tmem_ld_x16(d_tmem + c, x);
+                            tmem_ld_wait();
+                            int key = INT32_MIN;
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const int k0 = c + j < P.n_classes ? (int)v[j] * 16 + (15 - j) : INT32_MIN;
-                    const int k1 = c + j + 1 < P.n_classes ? (int)v[j + 1] * 16 + (14 - j) : INT32_MIN;
-                    key = __vimax3_s32(key, k0, k1);
-                }
-                const int cx = key >> 4;
-                if (cx > best) { best = cx; pos = c + 15 - (key & 15); }
-                int32_t *dst = full_tile ? stage_out + row_in_tile * P.n_classes + c : P.logits + img * P.n_classes + c;
-                if (full_tile || img < P.n) {
+                            for (int j = 0; j < 16; j += 2) {
+                                const int k0 = c + j < P.n_classes ? (int)x[j] * 16 + (15 - j) : INT32_MIN;
+                                const int k1 = c + j + 1 < P.n_classes ? (int)x[j + 1] * 16 + (14 - j) : INT32_MIN;
+                                key = __vimax3_s32(key, k0, k1);
+                            }
+                            const int cx = key >> 4;
+                            if (cx > best) { best = cx; pos = c + 15 - (key & 15); }
+                            int32_t *dst = full_tile ? stage_out + lane * P.n_classes + c : P.logits + img * P.n_classes + c;
+                            if (full_tile || img < P.n) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (c + j < P.n_classes) dst[j] = (int)v[j];
+                                for (int j = 0; j < 16; j++)
+                                    if (c + j < P.n_classes) dst[j] = (int)x[j];
+                            }
+                        }
+                        if (P.labels && img < P.n) P.labels[img] = pos;
+                        if (full_tile) {
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                bulk_store_1d(P.logits + ((size_t)tile * kTileM + quarter * 32) * P.n_classes, stage_out, warp_stage_bytes);
+                                bulk_commit();
+                            }
+                            store_pending |= 1u << q;
+                        }
+                    }
+                    // this warp's TMEM reads of D (and writes of A) are complete: tell the issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_ready[g][q]);
+                    BNM_TRACE_POINT();   // step end
                 }
-            }
-            if (P.labels && img < P.n) P.labels[img] = pos;
-            tc_fence_before();
-            if (full_tile) {
-                fence_proxy_async_smem();
-                named_bar_sync(1 + g, 128);
-                if (wg_tid == 0) {
-                    bulk_store_1d(P.logits + (size_t)tile * kTileM * P.n_classes, stage_out, P.out_stage_bytes);
-                    bulk_commit();
-                }
-                store_pending = true;
-            } else {
-                named_bar_sync(1 + g, 128);   // TMEM reads done before the next tile's MMA overwrites D
-            }
-            BNM_TRACE_POINT();   // tile end
-        }
-        if (store_pending && wg_tid == 0) bulk_wait_all<0>();
+        if (lane == 0) bulk_wait_all<0>();
     }
 
     tc_fence_before();
@@ -393,19 +422,25 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     p.tmem_a_off = round_up(d_cols, 32);
     p.tmem_wg_cols = p.tmem_a_off + round_up(std::max(a_cols, 1u), 16);
     if (p.tmem_wg_cols > 512) { delete plan; return fail("fused path: model does not fit the 512 TMEM columns"); }
-    p.n_wg = std::min<uint32_t>(kMaxWG, 512 / p.tmem_wg_cols);
-    if (const char *e = getenv("BNM_WG")) p.n_wg = std::max(1, std::min<int>((int)p.n_wg, atoi(e)));   // tuning knob
+    {   // tiles in flight per CTA = n_wg warpgroups x n_slots slots, bounded by the 512 TMEM columns
+        const uint32_t fit = 512 / p.tmem_wg_cols;
+        p.n_wg = std::min<uint32_t>(kMaxWG, fit);
+        p.n_slots = std::min<uint32_t>(kMaxSlots, fit / p.n_wg);
+        if (fit >= 4 && fit < 6) { p.n_wg = 2; p.n_slots = 2; }
+        if (const char *e = getenv("BNM_WG")) p.n_wg = std::max(1, std::min<int>((int)p.n_wg, atoi(e)));          // tuning knobs
+        if (const char *e = getenv("BNM_SLOTS")) p.n_slots = std::max(1, std::min<int>((int)std::min<uint32_t>(kMaxSlots, fit / p.n_wg), atoi(e)));
+    }
     p.out_stage_bytes = round_up(kTileM * p.n_classes * 4, 128);
     const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*static*/;
     p.off_w = 0;  // set below: stages first (1024-aligned), then weights, then staging
-    uint32_t fixed = round_up(p.w_bytes, 128) + p.n_wg * p.out_stage_bytes;
+    uint32_t fixed = round_up(p.w_bytes, 128) + p.n_wg * p.n_slots * p.out_stage_bytes;
     if (fixed + 2 * p.stage_bytes > smem_limit) { delete plan; return fail("fused path: weights do not fit in shared memory"); }
     p.n_stages = std::min<uint32_t>(kMaxStages, (smem_limit - fixed) / p.stage_bytes);
     p.n_stages = std::min<uint32_t>(p.n_stages, 6);
     p.off_w = p.n_stages * p.stage_bytes;
     p.off_out = p.off_w + round_up(p.w_bytes, 128);
-    plan->smem_bytes = (size_t)p.off_out + p.n_wg * p.out_stage_bytes + 1024;
-    plan->threads = p.n_wg * 128;
+    plan->smem_bytes = (size_t)p.off_out + p.n_wg * p.n_slots * p.out_stage_bytes + 1024;
+    plan->threads = p.n_wg * 160;   // 4 epilogue warps + 1 issuer warp per warpgroup
     plan->in_bytes = in_bytes;
     plan->sm_count = sm_count;
     plan->device = device;
@@ -428,8 +463,10 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     if (cudaDeviceSynchronize() != cudaSuccess) { fc_chain_plan_destroy(plan); return fail("weight image kernel failed"); }
     p.w_image = plan->d_w_image;
     p.err = plan->d_err;
-    if (cudaFuncSetAttribute(fc_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(fc_chain_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
         return fail("cannot opt in to the required dynamic shared memory");
     }
@@ -466,8 +503,13 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     const char *trace_path = getenv("BNM_TRACE");
     if (trace_path) { cudaMalloc(&d_trace, 1024 * sizeof(long long)); cudaMemset(d_trace, 0, 1024 * sizeof(long long)); }
     p.trace = d_trace;
-    if (p.n_wg <= 4) fc_chain_kernel<4><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
-    else fc_chain_kernel<6><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+    if (trace_path) {
+        if (p.n_slots == 1) fc_chain_kernel<1, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+        else fc_chain_kernel<2, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+    } else {
+        if (p.n_slots == 1) fc_chain_kernel<1, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+        else fc_chain_kernel<2, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+    }
     if (trace_path) {   // diagnostics only: synchronous dump of the phase clocks
         std::vector<long long> h(1024);
         cudaStreamSynchronize(st);

@@ -33,13 +33,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes (or the hint
+// expires) instead of re-issuing the probe -- waiting warps then cost no issue slots
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+    return ok != 0;
+}
 // Bounded wait: a wrong byte count / descriptor must not hang the GPU box.  On timeout the error word is
 // set and the kernel traps (the host then reports a launch failure instead of spinning forever).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err_flag = nullptr, int code = 1) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) {
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++spins > (1u << 20)) {
             if (err_flag) atomicExch(err_flag, code);
             __threadfence_system();
             asm volatile("trap;");

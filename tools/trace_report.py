@@ -1,14 +1,15 @@
 import sys, numpy as np
 t = np.array([int(x) for x in open(sys.argv[1]).read().split()], dtype=np.int64)
-n_layers = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-per = 2 + 4 * (n_layers - 1) + 2
-names = ["start->L1 issued(incl. wait for image)", "L1 MMA wait"]
-for l in range(1, n_layers):
-    names += [f"relunorm{l} (own)", f"relunorm{l} wg barrier", f"issue MMA{l+1}", f"MMA{l+1} wait"]
-names += ["final epilogue+store"]
-nt = len(t) // per
-d = np.diff(t[: nt * per].reshape(nt, per), axis=1)
-print(f"{nt} tiles of warpgroup 0 / CTA 0; cycles per phase (median over tiles 2..):")
-for k, nme in enumerate(names):
-    print(f"  {nme:42s} {np.median(d[2:, k]):8.0f}   (min {d[2:, k].min():6d} max {d[2:, k].max():6d})")
-print("  tile period (start to next start):", np.median(np.diff(t[0::per][:nt])))
+L = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+per = 3 * L * S
+nr = len(t) // per
+if nr < 3:
+    print("too few rounds", len(t)); sys.exit(0)
+a = t[: nr * per].reshape(nr, L, S, 3)
+print(f"{nr} rounds of warp 0 (warpgroup 0): median cycles, rounds 1..")
+for l in range(L):
+    for q in range(S):
+        w = np.median(a[1:, l, q, 1] - a[1:, l, q, 0]); k = np.median(a[1:, l, q, 2] - a[1:, l, q, 1])
+        print(f"  layer {l+1} slot {q}: wait for MMA {w:6.0f}   epilogue {k:6.0f}")
+print("  round period:", np.median(np.diff(a[:, 0, 0, 0])), "cycles for", S, "tiles per warpgroup")
