@@ -218,15 +218,36 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
+    const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
+    const uint32_t my_tiles = tile0 < P.n_tiles ? (P.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+    const uint32_t n_virt = n_wg * kSlots;                 // tiles in flight per CTA
+    const uint32_t n_rounds = (my_tiles + n_virt - 1) / n_virt;
+    const uint32_t w_base = smem_base + P.off_w;
+
+    // Image tile i of this CTA lives in ring stage i % n_st and belongs to slot (i % n_virt).  The first n_st loads are
+    // issued during setup (before the weights are staged, so HBM latency overlaps the prologue); afterwards the warp that
+    // has just seen the layer-1 MMAs of tile i complete (stage free) refills the stage with tile i + n_st.  Ring round
+    // u = i / n_st signals barrier bar_full[u & 1][s] (phase (u >> 1) & 1): with two barriers per stage a parity wait
+    // stays unambiguous even when a slot runs a whole round ahead of the loads.
+    const uint64_t l2_policy = policy_evict_first();   // images are read exactly once
+    auto issue_tile_load = [&](uint32_t i) {
+        const uint32_t s = i % n_st;
+        uint64_t *bar = &bar_full[(i / n_st) & 1][s];
+        mbar_arrive_expect_tx(bar, P.stage_bytes);
+        const int32_t row = (int32_t)((tile0 + i * tile_step) * kTileM);
+        for (uint32_t a = 0; a < P.in_atoms; a++)
+            tma_load_2d_hint(smem + s * P.stage_bytes + a * 16384, &tmap_in, (int32_t)(a * 128), row, bar, l2_policy);
+    };
+
     // ---------------- one-time setup
     if (tid == 0) {
         for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[0][s], 1); mbar_init(&bar_full[1][s], 1); }
         for (uint32_t g = 0; g < n_wg; g++)
             for (int q = 0; q < kSlots; q++) { mbar_init(&bar_mma[g][q], 1); mbar_init(&bar_ready[g][q], 4); }
         fence_mbar_init();
-        tma_prefetch_desc(&tmap_in);
+        for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
     }
-    if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+    if (warp == 1) tmem_alloc<512>(&tmem_base_s);
     {   // weight image -> smem (same bytes for every CTA; L2-resident after the first wave)
         const uint4 *src = reinterpret_cast<const uint4 *>(P.w_image);
         uint4 *dst = reinterpret_cast<uint4 *>(smem + P.off_w);
@@ -237,28 +258,6 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-
-    const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
-    const uint32_t my_tiles = tile0 < P.n_tiles ? (P.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
-    const uint32_t n_virt = n_wg * kSlots;                 // tiles in flight per CTA
-    const uint32_t n_rounds = (my_tiles + n_virt - 1) / n_virt;
-    const uint32_t w_base = smem_base + P.off_w;
-
-    // Image tile i of this CTA lives in ring stage i % n_st and belongs to slot (i % n_virt).  The first n_st loads are
-    // issued here; afterwards the warp that has just seen the layer-1 MMAs of tile i complete (stage free) refills the
-    // stage with tile i + n_st.  Ring round u = i / n_st signals barrier bar_full[u & 1][s] (phase (u >> 1) & 1): with
-    // two barriers per stage a parity wait stays unambiguous even when a slot runs a whole round ahead of the loads.
-    const uint64_t l2_policy = policy_evict_first();   // images are read exactly once
-    auto issue_tile_load = [&](uint32_t i) {
-        const uint32_t s = i % n_st;
-        uint64_t *bar = &bar_full[(i / n_st) & 1][s];
-        mbar_arrive_expect_tx(bar, P.stage_bytes);
-        const int32_t row = (int32_t)((tile0 + i * tile_step) * kTileM);
-        for (uint32_t a = 0; a < P.in_atoms; a++)
-            tma_load_2d_hint(smem + s * P.stage_bytes + a * 16384, &tmap_in, (int32_t)(a * 128), row, bar, l2_policy);
-    };
-    if (tid == 0)
-        for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
 
     if (warp >= n_wg * 4 && warp < n_wg * 5) {
         // ======================= MMA issuer warp of warpgroup g =======================
@@ -370,7 +369,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem_base);
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------
