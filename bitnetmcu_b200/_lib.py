@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbitnetmcu_b200.so")
+LIB_PATH = os.environ.get("BNM_LIB_PATH") or os.path.join(HERE, "libbitnetmcu_b200.so")   # override: tuning builds only
 
 # every symbol include/bitnetmcu_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED = [

@@ -116,6 +116,41 @@ __device__ __forceinline__ int max16(const uint32_t (&v)[16], int m) {
     return max(m, m2);
 }
 
+// hidden-layer epilogue, the common 64-wide case: one TMEM load of the whole row, one TMEM store of the 16 packed words
+__device__ __forceinline__ void relunorm_tmem64(uint32_t d_addr, uint32_t a_addr) {
+    uint32_t v[64];
+#ifdef BNM_LD_X16
+    {
+        uint32_t (&v4)[4][16] = reinterpret_cast<uint32_t (&)[4][16]>(v);
+#pragma unroll
+        for (int c = 0; c < 4; c++) tmem_ld_x16(d_addr + 16 * c, v4[c]);
+    }
+#else
+    tmem_ld_x64(d_addr, v);
+#endif
+    tmem_ld_wait();
+    int mc[4];   // four independent max chains (ILP), merged at the end
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int m = 0, m2 = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            m = __vimax3_s32(m, (int)v[16 * c + j], (int)v[16 * c + j + 1]);
+            m2 = __vimax3_s32(m2, (int)v[16 * c + j + 2], (int)v[16 * c + j + 3]);
+        }
+        mc[c] = max(m, m2);
+    }
+    const NormCoef k = norm_coef(max(__vimax3_s32(mc[0], mc[1], mc[2]), mc[3]));
+#pragma unroll
+    for (int h = 0; h < 2; h++) {   // two 8-word stores keep the register peak below the 128-register budget
+        uint32_t w[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) w[q] = norm_pack4(v[32 * h + 4 * q], v[32 * h + 4 * q + 1], v[32 * h + 4 * q + 2], v[32 * h + 4 * q + 3], k);
+        tmem_st_x8(a_addr + 8 * h, w);
+    }
+    tmem_st_wait();
+}
+
 // hidden-layer epilogue: D[tmem, n_pad columns] -> A[tmem, n_pad/4 columns]
 template <bool kOnePass>
 __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, uint32_t n_pad) {
@@ -177,9 +212,14 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
 //     while the MMAs of slot X are in flight the epilogue warps requantise slot Y, so the integer ALU work of
 //     ReLUNorm -- the real limiter of this kernel -- is never parked behind tensor-pipe latency.
 // Barriers: full[2][stage] (TMA tile landed), mma[g][slot] (MMA batch complete -> epilogue may read D),
-//           ready[g][slot] (4 arrivals: every epilogue warp has written A / finished reading D -> issuer may go on).
+//           ready[g][slot] (128 arrivals: every epilogue thread has written A / finished reading D -> issuer may go on).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 2;
+#ifndef BNM_ARRIVE_ELECTED
+constexpr uint32_t kReadyArrivals = 128;   // every epilogue thread arrives
+#else
+constexpr uint32_t kReadyArrivals = 4;     // one elected lane per epilogue warp arrives
+#endif
 
 // layer-1 MMAs: A = image tile in smem (SWIZZLE_128B K-major), B = weight tiles.  Whole warp converged so that all
 // descriptor arithmetic stays in the uniform datapath; only the tcgen05 instructions are predicated on one lane.
@@ -243,7 +283,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     if (tid == 0) {
         for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[0][s], 1); mbar_init(&bar_full[1][s], 1); }
         for (uint32_t g = 0; g < n_wg; g++)
-            for (int q = 0; q < kSlots; q++) { mbar_init(&bar_mma[g][q], 1); mbar_init(&bar_ready[g][q], 4); }
+            for (int q = 0; q < kSlots; q++) { mbar_init(&bar_mma[g][q], 1); mbar_init(&bar_ready[g][q], kReadyArrivals); }
         fence_mbar_init();
         for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
     }
@@ -292,32 +332,41 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         const uint32_t g = warp >> 2, quarter = warp & 3;
         const uint32_t lane_sel = (quarter * 32) << 16;
         const uint32_t warp_stage_bytes = 32 * P.n_classes * 4;
-        uint32_t mma_phase = 0, store_pending = 0;   // one bit per slot (keeps the slot loop rolled: code size / I-cache)
+        // slot-0 constants in registers; slot q adds a multiple (the slot loop stays rolled: one copy of the code in the I-cache)
+        const uint32_t slot_cols = P.tmem_wg_cols, slot_stage = 4 * warp_stage_bytes;
+        const uint32_t d_tm0 = tmem_base + g * kSlots * slot_cols + lane_sel;
+        const uint32_t bar_mma0 = smem_u32(&bar_mma[g][0]), bar_ready0 = smem_u32(&bar_ready[g][0]);
+        uint8_t *const stage0 = smem + P.off_out + (g * kSlots * 4 + quarter) * warp_stage_bytes;
+        const uint32_t a_off = P.tmem_a_off;
+        const int n_layers = P.n_layers;
+        uint32_t mma_phase = 0, store_pending = 0;   // one bit per slot
         const bool tracing = kTrace && P.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
         uint32_t trace_n = 0;
 #define BNM_TRACE_POINT() do { if (kTrace && tracing && trace_n < 1024) P.trace[trace_n++] = clock64(); } while (0)
 
-        for (uint32_t r = 0; r < n_rounds; r++)
-            for (int l = 0; l < P.n_layers; l++)
+        for (uint32_t r = 0, i0 = g * kSlots; r < n_rounds; r++, i0 += n_virt)
+            for (int l = 0; l < n_layers; l++) {
+                const uint32_t n_pad_l = P.n_pad[l];
 #pragma unroll 1
                 for (int q = 0; q < kSlots; q++) {
-                    const uint32_t v = g * kSlots + q, i = r * n_virt + v;
+                    const uint32_t i = i0 + q;
                     if (i >= my_tiles) continue;
-                    const uint32_t d_tmem = tmem_base + v * P.tmem_wg_cols + lane_sel, a_tmem = d_tmem + P.tmem_a_off;
+                    const uint32_t d_tm = d_tm0 + q * slot_cols;
                     BNM_TRACE_POINT();   // step start
-                    mbar_wait(&bar_mma[g][q], (mma_phase >> q) & 1, P.err, 3);
+                    mbar_wait_a(bar_mma0 + q * 8, (mma_phase >> q) & 1, P.err, 3);
                     mma_phase ^= 1u << q;
                     tc_fence_after();
                     BNM_TRACE_POINT();   // MMAs of layer l+1 complete
-                    if (l == 0 && quarter == 1 && i + n_st < my_tiles && elect_one()) issue_tile_load(i + n_st);   // stage is free
-                    if (l + 1 < P.n_layers) {
-                        relunorm_tmem<true>(d_tmem, a_tmem, P.n_pad[l]);
+                    if (l + 1 < n_layers) {
+                        if (l == 0 && quarter == 1 && i + n_st < my_tiles && elect_one()) issue_tile_load(i + n_st);   // stage is free
+                        if (n_pad_l == 64) relunorm_tmem64(d_tm, d_tm + a_off);
+                        else relunorm_tmem<true>(d_tm, d_tm + a_off, n_pad_l);
                     } else {
                         // ---- logits + label (dll.c:115-116: the last ReLUNorm's argmax is what Inference() returns)
                         const uint32_t tile = tile0 + i * tile_step;
                         const size_t img = (size_t)tile * kTileM + quarter * 32 + lane;
                         const bool full_tile = (size_t)(tile + 1) * kTileM <= P.n;
-                        int32_t *stage_out = reinterpret_cast<int32_t *>(smem + P.off_out + (v * 4 + quarter) * warp_stage_bytes);
+                        int32_t *stage_out = reinterpret_cast<int32_t *>(stage0 + q * slot_stage);
                         if ((store_pending >> q) & 1) {   // the previous bulk store of this slot must have finished reading the staging rows
                             if (lane == 0) bulk_wait_read<kSlots - 1>();
                             __syncwarp();
@@ -329,7 +378,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                         uint32_t pos = 255;
                         for (uint32_t c = 0; c < P.n_classes; c += 16) {
                             uint32_t x[16];
-                            tmem_ld_x16(d_tmem + c, x);
+                            tmem_ld_x16(d_tm + c, x);
                             tmem_ld_wait();
                             int key = INT32_MIN;
 #pragma unroll
@@ -358,12 +407,17 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                             store_pending |= 1u << q;
                         }
                     }
-                    // this warp's TMEM reads of D (and writes of A) are complete: tell the issuer
+                    // this thread's TMEM reads of D (and writes of A) are complete: tell the issuer (128 arrivals per step)
                     tc_fence_before();
+#ifndef BNM_ARRIVE_ELECTED   // measured: 128 fire-and-forget arrivals beat syncwarp + one elected arrival (fewer instructions per step)
+                    mbar_arrive_a(bar_ready0 + q * 8);
+#else
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_ready[g][q]);
+                    if (lane == 0) mbar_arrive_a(bar_ready0 + q * 8);
+#endif
                     BNM_TRACE_POINT();   // step end
                 }
+            }
         if (lane == 0) bulk_wait_all<0>();
     }
 

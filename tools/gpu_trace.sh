@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
 for cfg in ${CFGS:-"3 2" "3 1" "2 2"}; do
-set -- $cfg
+set -- ${cfg/_/ }
 BNM_WG=$1 BNM_SLOTS=$2 BNM_TRACE=gpurun_out/trace_wg$1_s$2.txt timeout 120 python - <<'PY'
 import os, sys, numpy as np
 sys.path.insert(0, '.')
