@@ -142,6 +142,8 @@ __device__ __forceinline__ void relunorm_tmem64(uint32_t d_addr, uint32_t a_addr
         mc[c] = max(m, m2);
     }
     const NormCoef k = norm_coef(max(__vimax3_s32(mc[0], mc[1], mc[2]), mc[3]));
+    // (an IMAD.HI + I2IP.S8.SAT formulation that moves shift/round/clip to the FMA pipe is bit-exact too but measured
+    //  slower in this kernel for every ALU/FMA split: tools/requant_bench.cu, profiles/r1_micro_requant.txt)
 #pragma unroll
     for (int h = 0; h < 2; h++) {   // two 8-word stores keep the register peak below the 128-register budget
         uint32_t w[8];
@@ -179,22 +181,38 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
         // two passes over TMEM (wide layers such as Binary-160, and the high-occupancy variant where 64
         // accumulators per thread would not fit the register budget): max first, then requantise
         int m = 0;
+        const uint32_t n32 = n_pad & ~31u;   // 32-column chunks, then at most one 16-column tail
 #pragma unroll 1
-        for (uint32_t c = 0; c < n_pad; c += 16) {
+        for (uint32_t c = 0; c < n32; c += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(d_addr + c, v);
+            tmem_ld_wait();
+            m = max16(reinterpret_cast<const uint32_t (&)[16]>(v[0]), m);
+            m = max16(reinterpret_cast<const uint32_t (&)[16]>(v[16]), m);
+        }
+        if (n32 < n_pad) {
             uint32_t v[16];
-            tmem_ld_x16(d_addr + c, v);
+            tmem_ld_x16(d_addr + n32, v);
             tmem_ld_wait();
             m = max16(v, m);
         }
         const NormCoef k = norm_coef(m);
 #pragma unroll 1
-        for (uint32_t c = 0; c < n_pad; c += 16) {
+        for (uint32_t c = 0; c < n32; c += 32) {
+            uint32_t v[32], w[8];
+            tmem_ld_x32(d_addr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; q++) w[q] = norm_pack4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], k);
+            tmem_st_x8(a_addr + (c >> 2), w);
+        }
+        if (n32 < n_pad) {
             uint32_t v[16], w[4];
-            tmem_ld_x16(d_addr + c, v);
+            tmem_ld_x16(d_addr + n32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 4; q++) w[q] = norm_pack4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], k);
-            tmem_st_x4(a_addr + (c >> 2), w);
+            tmem_st_x4(a_addr + (n32 >> 2), w);
         }
     }
     tmem_st_wait();

@@ -252,9 +252,10 @@ void launch_maxpool22(const int32_t *act, uint32_t xy, int32_t *out, size_t n, c
 // ------------------------------------------------------------------------------------------------
 // Fused CNN front-end for the 16x16 geometry (BitNetMCU_MNIST_dll.c:64-80).
 // thread = (image, channel).  conv1 (int8 x int8) runs on dp4a over 4-byte sliding windows that are built
-// once per image in shared memory and broadcast to all channel threads; conv2/conv3 (int32 x int8) on IMAD
-// with rolling line buffers in registers; pools folded in; ReLUNorm over the C*4 features of an image via a
-// shared-memory max.  n_shift is the literal 4 of dll.c:71-74.
+// once per image in shared memory and broadcast to all channel threads; conv2 (conv1 outputs are < 2^15: int8 x int8
+// x 9 >> 4 <= 9216) on dp2a over packed int16 pairs, 2 instructions per kernel row instead of 3 IMADs; conv3
+// (int32 x int8) on IMAD; rolling line buffers in registers; pools folded in; ReLUNorm over the C*4 features of
+// an image via a shared-memory max.  n_shift is the literal 4 of dll.c:71-74.  Bound: the FMA pipe (IMAD/IDP issue).
 // ------------------------------------------------------------------------------------------------
 constexpr int kCnnThreads = 256;
 
@@ -270,14 +271,16 @@ __global__ void __launch_bounds__(kCnnThreads) k_cnn_frontend16(const int8_t *__
     const bool active = t < ipb * C;
     const uint32_t il = active ? t / C : 0, ch = active ? t % C : 0;
 
-    int w1p[3], k2[9], k3[9];
+    int w1p[3], w2p[3], k3[9];   // per kernel row: (w0, w1, w2, 0) packed as int8x4
     {
         const int8_t *a = w1 + ch * 9, *b = w2 + ch * 9, *c = w3 + ch * 9;
 #pragma unroll
-        for (int r = 0; r < 3; r++)
+        for (int r = 0; r < 3; r++) {
             w1p[r] = (int)((uint32_t)(uint8_t)a[3 * r] | ((uint32_t)(uint8_t)a[3 * r + 1] << 8) | ((uint32_t)(uint8_t)a[3 * r + 2] << 16));
+            w2p[r] = (int)((uint32_t)(uint8_t)b[3 * r] | ((uint32_t)(uint8_t)b[3 * r + 1] << 8) | ((uint32_t)(uint8_t)b[3 * r + 2] << 16));
+        }
 #pragma unroll
-        for (int i = 0; i < 9; i++) { k2[i] = b[i]; k3[i] = c[i]; }
+        for (int i = 0; i < 9; i++) k3[i] = c[i];
     }
 
     const size_t n_groups = (n + ipb - 1) / ipb;
@@ -300,19 +303,23 @@ __global__ void __launch_bounds__(kCnnThreads) k_cnn_frontend16(const int8_t *__
         int f[4] = {0, 0, 0, 0};
         if (active) {
             const uint32_t *win = s_win + il * 224;
-            int c1[3][14];   // rolling conv1 rows
+            uint32_t c1[3][14];   // rolling conv1 rows as int16 pairs: c1[.][x] = (v[x], v[x+1]), c1[.][13] = (v[13], 0)
             int c2e[12];     // even conv2 row awaiting its odd partner
             int pl[3][6];    // rolling pooled rows
             int c3e[4];
 #pragma unroll
             for (int y = 0; y < 14; y++) {
+                int v1[14];
 #pragma unroll
                 for (int x = 0; x < 14; x++) {
                     int s = __dp4a((int)win[(y + 0) * 14 + x], w1p[0], 0);
                     s = __dp4a((int)win[(y + 1) * 14 + x], w1p[1], s);
                     s = __dp4a((int)win[(y + 2) * 14 + x], w1p[2], s);
-                    c1[y % 3][x] = max(s, 0) >> 4;
+                    v1[x] = max(s, 0) >> 4;
                 }
+#pragma unroll
+                for (int x = 0; x < 13; x++) c1[y % 3][x] = __byte_perm((uint32_t)v1[x], (uint32_t)v1[x + 1], 0x5410);
+                c1[y % 3][13] = (uint32_t)v1[13];
                 if (y >= 2) {
                     const int r = y - 2;  // conv2 output row
                     int v[12];
@@ -320,9 +327,10 @@ __global__ void __launch_bounds__(kCnnThreads) k_cnn_frontend16(const int8_t *__
                     for (int x = 0; x < 12; x++) {
                         int s = 0;
 #pragma unroll
-                        for (int dr = 0; dr < 3; dr++)
-#pragma unroll
-                            for (int dc = 0; dc < 3; dc++) s += k2[3 * dr + dc] * c1[(r + dr) % 3][x + dc];
+                        for (int dr = 0; dr < 3; dr++) {   // taps 0,1 from the pair at x, tap 2 from the pair at x+2
+                            s = __dp2a_lo((int)c1[(r + dr) % 3][x], w2p[dr], s);
+                            s = __dp2a_hi((int)c1[(r + dr) % 3][x + 2], w2p[dr], s);
+                        }
                         v[x] = max(s, 0) >> 4;
                     }
                     if ((r & 1) == 0) {

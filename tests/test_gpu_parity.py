@@ -256,3 +256,65 @@ def test_reference_named_symbols(lib, oracle):
     wantp = oracle.maxpool22(buf[:196], 14)
     end = lib.processmaxpool22(C.c_void_p(buf.ctypes.data), 14, C.c_void_p(buf.ctypes.data))
     assert end == buf.ctypes.data + 49 * 4 and np.array_equal(buf[:49], wantp)
+
+
+# ---- worst-case magnitudes (SURVEY.md section 7 "Bit-exact corner cases" and range bounds) ------------------------
+
+def _extreme_images():
+    rng = np.random.default_rng(123)
+    imgs = np.empty((400, 256), dtype=np.int8)
+    imgs[:100] = -128
+    imgs[100:200] = 127
+    imgs[200:300] = rng.choice(np.array([-128, 127], dtype=np.int8), size=(100, 256))
+    imgs[300:] = rng.integers(-128, 128, size=(100, 256))
+    return imgs
+
+
+@pytest.mark.parametrize("enc_name", ["4bitsym", "8bit", "FP130", "Binary", "2bitsym"])
+def test_extreme_weights_fc(lib, oracle, enc_name):
+    """All weights at the largest magnitude of the encoding (both signs), images at the int8 rails: the accumulators hit
+    256*128*15 = 491 520 (4bitsym) / 4.2 M (8bit, FP130 incl. the +128 residual plane); rows with max < 128 (shift 0) and
+    all-negative rows occur too."""
+    from bitnetmcu_b200 import _lib, model as M, pack as P
+    from bitnetmcu_b200.engine import Engine
+    enc = P.QUANT_IDS[enc_name]
+    lut = P.INT_LUT[enc]
+    hi, lo = int(np.argmax(lut)), int(np.argmin(lut))
+    rng = np.random.default_rng(7)
+    layers = []
+    widths = (256, 64, 64, 64, 10)
+    for i in range(4):
+        codes = rng.choice(np.array([hi, lo], dtype=np.uint32), size=(widths[i + 1], widths[i]), p=[0.6, 0.4])
+        if i == 1:
+            codes[:8] = lo          # some all-negative rows
+        layers.append(P.fc_layer_from_codes(f"L{i + 1}", enc, codes))
+    m = M.Model(model_class=M.MODEL_FCMNIST, layers=layers)
+    imgs = _extreme_images()
+    want_logits, want_labels = oracle.infer(m, imgs)
+    assert np.abs(want_logits).max() > 1000
+    for path in (_lib.PATH_LAYERS, _lib.PATH_TCGEN05):
+        e = Engine(m, path=path)
+        lo_, la_ = e.infer(imgs)
+        assert np.array_equal(lo_, want_logits) and np.array_equal(la_, want_labels), path
+        e.close()
+
+
+def test_extreme_weights_cnn(lib, oracle):
+    """conv weights at -128 / 127 and images at the rails: conv1 reaches its bound 9*128*128>>4 = 9216 (int16 pairs for the
+    dp2a conv2), conv2 663 552, conv3 up to 4.7e7."""
+    from bitnetmcu_b200 import model as M
+    from bitnetmcu_b200.engine import Engine
+    base = load_model("cnn_48")
+    rng = np.random.default_rng(9)
+    for l in base.layers:
+        if l.kind == M.LAYER_CONV33:
+            w = rng.choice(np.array([-128, 127], dtype=np.int8), size=l.weights.shape)
+            w[:9] = -128
+            w[9:18] = 127
+            l.weights = w
+    imgs = _extreme_images()
+    want_logits, want_labels = oracle.infer(base, imgs)
+    e = Engine(base)
+    lo_, la_ = e.infer(imgs)
+    assert np.array_equal(lo_, want_logits) and np.array_equal(la_, want_labels)
+    e.close()

@@ -31,9 +31,9 @@ __device__ __forceinline__ uint32_t packA(uint32_t x0, uint32_t x1, uint32_t x2,
     return __byte_perm(lo, hi, 0x5410);
 }
 __device__ __forceinline__ int hiB(uint32_t x, const Coef &c) {
-    long long d;
-    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"((int)x), "r"(c.mw), "l"(c.cw));
-    return (int)(d >> 32);
+    int d;   // t = (x >> (s-1)) - 127 = hi32(x * 2^(33-s)) - 127: ONE IMAD.HI (FMA pipe)
+    asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(d) : "r"((int)x), "r"(c.mw), "r"(-127));
+    return d;
 }
 __device__ __forceinline__ uint32_t packB(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, const Coef &c) {
     int t0 = hiB(x0, c), t1 = hiB(x1, c), t2 = hiB(x2, c), t3 = hiB(x3, c);
@@ -49,7 +49,7 @@ __device__ __forceinline__ int max16(const uint32_t *v, int m) {
     return max(m, m2);
 }
 
-template <int VAR> __global__ void k(const int *in, uint32_t *out, long long *cyc, int iters) {
+template <int NB> __global__ void k(const int *in, uint32_t *out, long long *cyc, int iters) {
     uint32_t v[64];
     for (int i = 0; i < 64; i++) v[i] = in[(threadIdx.x % 256) * 64 + i];
     uint32_t acc[16] = {0};
@@ -60,23 +60,25 @@ template <int VAR> __global__ void k(const int *in, uint32_t *out, long long *cy
 #pragma unroll
         for (int c = 0; c < 4; c++) mc[c] = max16(v + 16 * c, 0);
         Coef k = coef(max(__vimax3_s32(mc[0], mc[1], mc[2]), mc[3]));
+        if (NB > 0 && __all_sync(0xffffffffu, k.shift >= 3)) {
 #pragma unroll
-        for (int w = 0; w < 16; w++) {
-            uint32_t r;
-            const bool useA = VAR == 0 || (VAR == 2 && (w & 3) == 3) || (VAR >= 1 && k.shift < 3);
-            if (VAR == 0) r = packA(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k);
-            else if (VAR == 1) r = k.shift >= 3 ? packB(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k) : packA(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k);
-            else r = (k.shift >= 3 && (w & 3) != 3) ? packB(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k) : packA(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k);
-            (void)useA;
-            acc[w] ^= r;
+            for (int w = 0; w < 16; w++) {
+                uint32_t r = (w & 3) < NB ? packB(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k)
+                                          : packA(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k);
+                acc[w] ^= r;
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 16; w++) acc[w] ^= packA(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k);
         }
-#pragma unroll
-        for (int i = 0; i < 64; i++) v[i] += (acc[i & 15] & 1);   // loop-carried dependency so nothing is hoisted
+        v[it & 63] += (acc[it & 15] & 1);   // light loop-carried dependency
     }
     long long t1 = clock64();
     for (int w = 0; w < 16; w++) out[threadIdx.x * 16 + w] = acc[w];
     if (threadIdx.x == 0) cyc[0] = t1 - t0;
 }
+
+template <int NB> void launch(const int *din, uint32_t *dout, long long *dc, int nt, int iters) { k<NB><<<1, nt>>>(din, dout, dc, iters); }
 
 int main() {
     const int NT = 512;
@@ -84,6 +86,7 @@ int main() {
     srand(1);
     for (int r = 0; r < 256; r++) {
         int scale = 1 << (5 + r % 16);
+        if (getenv("BIGROWS")) scale = 1 << (12 + r % 8);
         for (int i = 0; i < 64; i++) h[r * 64 + i] = (rand() % (2 * scale)) - scale;
         if (r % 7 == 0) h[r * 64 + 5] = (128 << (r % 12)) - 1;           // top-of-bucket values: the (x+r)>>s == 128 clip case
         if (r % 11 == 0) for (int i = 0; i < 64; i++) h[r * 64 + i] = -abs(h[r * 64 + i]) - 1;
@@ -92,10 +95,10 @@ int main() {
     CK(cudaMalloc(&din, 256 * 64 * 4)); CK(cudaMalloc(&dout, NT * 16 * 4)); CK(cudaMalloc(&dc, 8));
     CK(cudaMemcpy(din, h, 256 * 64 * 4, cudaMemcpyHostToDevice));
     uint32_t *ho = (uint32_t *)malloc(NT * 16 * 4);
-    const char *names[3] = {"A (VIADDMNMX+IMAD+PRMT)", "B (mad.wide+I2IP.S8+fix)", "M (3 words B + 1 word A)"};
-    for (int var = 0; var < 3; var++) {
+    const char *names[5] = {"4A+0B (VIADDMNMX+IMAD+PRMT)", "3A+1B", "2A+2B", "1A+3B", "0A+4B (IMAD.HI+I2IP.S8+fix)"};
+    for (int var = 0; var < 5; var++) {
         // correctness: one iteration
-        if (var == 0) k<0><<<1, 256>>>(din, dout, dc, 1); else if (var == 1) k<1><<<1, 256>>>(din, dout, dc, 1); else k<2><<<1, 256>>>(din, dout, dc, 1);
+        if (var == 0) launch<0>(din, dout, dc, 256, 1); else if (var == 1) launch<1>(din, dout, dc, 256, 1); else if (var == 2) launch<2>(din, dout, dc, 256, 1); else if (var == 3) launch<3>(din, dout, dc, 256, 1); else launch<4>(din, dout, dc, 256, 1);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(ho, dout, 256 * 16 * 4, cudaMemcpyDeviceToHost));
         long bad = 0;
@@ -112,7 +115,7 @@ int main() {
         printf("%-28s correctness: %ld mismatches of %d\n", names[var], bad, 256 * 64);
         for (int wps : {1, 2, 3, 4}) {
             int nt = 128 * wps;
-            if (var == 0) k<0><<<1, nt>>>(din, dout, dc, 200); else if (var == 1) k<1><<<1, nt>>>(din, dout, dc, 200); else k<2><<<1, nt>>>(din, dout, dc, 200);
+            if (var == 0) launch<0>(din, dout, dc, nt, 200); else if (var == 1) launch<1>(din, dout, dc, nt, 200); else if (var == 2) launch<2>(din, dout, dc, nt, 200); else if (var == 3) launch<3>(din, dout, dc, nt, 200); else launch<4>(din, dout, dc, nt, 200);
             CK(cudaDeviceSynchronize());
             long long c; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
             printf("    %d warps/SMSP: %7.1f cycles per 64-accumulator epilogue per warp  -> %6.1f per SMSP-epilogue\n", wps, c / 200.0, c / 200.0 / wps);
