@@ -154,32 +154,11 @@ __device__ __forceinline__ void relunorm_tmem64(uint32_t d_addr, uint32_t a_addr
     tmem_st_wait();
 }
 
-// hidden-layer epilogue: D[tmem, n_pad columns] -> A[tmem, n_pad/4 columns]
-template <bool kOnePass>
+// hidden-layer epilogue for every other width: D[tmem, n_pad columns] -> A[tmem, n_pad/4 columns] in two passes over
+// TMEM (row maximum first, then requantise), 32 columns at a time -- wide layers (Binary-160) would not fit the
+// register budget in one pass, narrow ones (16..48) do not need it.
 __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, uint32_t n_pad) {
-    if (kOnePass && n_pad <= 64) {
-        // one pass: the whole row (<= 64 accumulators) stays in registers
-        uint32_t v[4][16];
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            if ((uint32_t)c * 16 < n_pad) tmem_ld_x16(d_addr + c * 16, v[c]);
-        tmem_ld_wait();
-        int mc[4] = {0, 0, 0, 0};   // four independent max chains (ILP), merged at the end
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            if ((uint32_t)c * 16 < n_pad) mc[c] = max16(v[c], 0);
-        const NormCoef k = norm_coef(max(__vimax3_s32(mc[0], mc[1], mc[2]), mc[3]));
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            if ((uint32_t)c * 16 < n_pad) {
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) w[q] = norm_pack4(v[c][4 * q], v[c][4 * q + 1], v[c][4 * q + 2], v[c][4 * q + 3], k);
-                tmem_st_x4(a_addr + c * 4, w);
-            }
-    } else {
-        // two passes over TMEM (wide layers such as Binary-160, and the high-occupancy variant where 64
-        // accumulators per thread would not fit the register budget): max first, then requantise
+    {
         int m = 0;
         const uint32_t n32 = n_pad & ~31u;   // 32-column chunks, then at most one 16-column tail
 #pragma unroll 1
@@ -377,7 +356,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                     if (l + 1 < n_layers) {
                         if (l == 0 && quarter == 1 && i + n_st < my_tiles && elect_one()) issue_tile_load(i + n_st);   // stage is free
                         if (n_pad_l == 64) relunorm_tmem64(d_tm, d_tm + a_off);
-                        else relunorm_tmem<true>(d_tm, d_tm + a_off, n_pad_l);
+                        else relunorm_tmem(d_tm, d_tm + a_off, n_pad_l);
                         // this thread's reads of D and writes of A are complete: tell the issuer (128 fire-and-forget arrivals per
                         // step; measured faster than syncwarp + one elected arrival: fewer instructions)
                         tc_fence_before();
