@@ -194,6 +194,8 @@ def main():
 
     rank, local_rank, world = bdist.env_rank_world()
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...", printed at NCCL_DEBUG=VERSION/INFO) off it
+        os.environ["NCCL_DEBUG"] = os.environ.get("BNM_NCCL_DEBUG", "WARN")
         bdist.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
