@@ -252,6 +252,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
+    if (kTrace && P.trace && blockIdx.x == 0 && tid == 0) P.trace[1020] = clock64();   // kernel entry
     const uint32_t n_wg = P.n_wg, n_st = P.n_stages;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -278,24 +279,39 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     };
 
     // ---------------- one-time setup
-    if (tid == 0) {
+    // One thread (lane 0 of the first issuer warp) initialises the barriers and issues the first image loads; it takes no
+    // part in staging the weights, so it never executes the generic->async proxy fence -- measured: that fence, executed by
+    // the thread that has TMA loads in flight, waits for them to land (~3 us per launch).
+    if (kTrace && P.trace && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1024 + 2 * blockIdx.x] = (long long)gt; }
+    const bool setup_thread = tid == n_wg * 128;
+    if (setup_thread) {
         for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[0][s], 1); mbar_init(&bar_full[1][s], 1); }
         for (uint32_t g = 0; g < n_wg; g++)
             for (int q = 0; q < kSlots; q++) { mbar_init(&bar_mma[g][q], 1); mbar_init(&bar_ready[g][q], kReadyArrivals); }
         fence_mbar_init();
+        if (kTrace && P.trace && blockIdx.x == 0) P.trace[1016] = clock64();   // barriers initialised
         for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
-    }
-    if (warp == 1) tmem_alloc<512>(&tmem_base_s);
-    {   // weight image -> smem (same bytes for every CTA; L2-resident after the first wave)
+        if (kTrace && P.trace && blockIdx.x == 0) P.trace[1017] = clock64();   // first loads issued
+    } else {
+        if (warp == 1) {
+            tmem_alloc<512>(&tmem_base_s);
+            if (kTrace && P.trace && blockIdx.x == 0 && lane == 0) P.trace[1018] = clock64();   // TMEM allocated
+        }
+        // weight image -> smem (same bytes for every CTA; L2-resident after the first wave)
         const uint4 *src = reinterpret_cast<const uint4 *>(P.w_image);
         uint4 *dst = reinterpret_cast<uint4 *>(smem + P.off_w);
+        // (the setup thread's share of the copy is taken by thread 0: indices congruent to its id)
         for (uint32_t i = tid; i < P.w_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        if (tid == 0)
+            for (uint32_t i = n_wg * 128; i < P.w_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        if (tid == 64 && kTrace && P.trace && blockIdx.x == 0) P.trace[1019] = clock64();   // weights staged (thread 64)
+        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
     }
-    fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    if (kTrace && P.trace && blockIdx.x == 0 && tid == 0) P.trace[1021] = clock64();   // prologue done
 
     if (warp >= n_wg * 4 && warp < n_wg * 5) {
         // ======================= MMA issuer warp of warpgroup g =======================
@@ -338,7 +354,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         uint32_t mma_phase = 0;   // one phase bit per slot
         const bool tracing = kTrace && P.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0;
         uint32_t trace_n = 0;
-#define BNM_TRACE_POINT() do { if (kTrace && tracing && trace_n < 1024) P.trace[trace_n++] = clock64(); } while (0)
+#define BNM_TRACE_POINT() do { if (kTrace && tracing && trace_n < 1000) P.trace[trace_n++] = clock64(); } while (0)
 
         for (uint32_t r = 0, i0 = g * kSlots; r < n_rounds; r++, i0 += n_virt)
             for (int l = 0; l < n_layers; l++) {
@@ -430,6 +446,8 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (kTrace && P.trace && blockIdx.x == 0 && tid == 0) P.trace[1022] = clock64();   // all roles done
+    if (kTrace && P.trace && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1025 + 2 * blockIdx.x] = (long long)gt; }
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
@@ -562,7 +580,7 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     unsigned grid = (unsigned)std::min<uint32_t>(p.n_tiles, (uint32_t)plan->sm_count);
     long long *d_trace = nullptr;
     const char *trace_path = getenv("BNM_TRACE");
-    if (trace_path) { cudaMalloc(&d_trace, 1024 * sizeof(long long)); cudaMemset(d_trace, 0, 1024 * sizeof(long long)); }
+    if (trace_path) { cudaMalloc(&d_trace, 2048 * sizeof(long long)); cudaMemset(d_trace, 0, 2048 * sizeof(long long)); }
     p.trace = d_trace;
     if (trace_path) {
         if (p.n_slots == 1) fc_chain_kernel<1, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
@@ -572,12 +590,23 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
         else fc_chain_kernel<2, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
     }
     if (trace_path) {   // diagnostics only: synchronous dump of the phase clocks
-        std::vector<long long> h(1024);
+        std::vector<long long> h(2048);
         cudaStreamSynchronize(st);
-        cudaMemcpy(h.data(), d_trace, 1024 * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaMemcpy(h.data(), d_trace, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(d_trace);
         if (FILE *f = fopen(trace_path, "w")) {
-            for (int i = 0; i < 1024 && h[i]; i++) fprintf(f, "%lld\n", h[i]);
+            for (int i = 0; i < 1000 && h[i]; i++) fprintf(f, "%lld\n", h[i]);
+            fprintf(f, "# entry %lld prologue_done %lld exit %lld\n", h[1020], h[1021], h[1022]);
+            {   // per-CTA lifetime from %globaltimer (ns): spread of entry and exit times over the grid
+                long long e0 = h[1024], e1 = h[1024], x0 = h[1025], x1 = h[1025];
+                for (unsigned b = 0; b < grid && b < 500; b++) {
+                    e0 = std::min(e0, h[1024 + 2 * b]); e1 = std::max(e1, h[1024 + 2 * b]);
+                    x0 = std::min(x0, h[1025 + 2 * b]); x1 = std::max(x1, h[1025 + 2 * b]);
+                }
+                fprintf(f, "## globaltimer ns: CTA entry spread %lld, first entry -> first exit %lld, first entry -> last exit %lld\n", e1 - e0, x0 - e0, x1 - e0);
+            }
+            fprintf(f, "## since entry: barriers %lld, loads issued %lld, tmem alloc %lld, weights staged %lld\n", h[1016] - h[1020], h[1017] - h[1020],
+                    h[1018] - h[1020], h[1019] - h[1020]);
             fclose(f);
         }
     }

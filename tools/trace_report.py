@@ -1,5 +1,12 @@
 import sys, numpy as np
-t = np.array([int(x) for x in open(sys.argv[1]).read().split()], dtype=np.int64)
+lines = open(sys.argv[1]).read().splitlines()
+t = np.array([int(x) for x in lines if x and not x.startswith('#')], dtype=np.int64)
+for l in lines:
+    if l.startswith('##'):
+        print(' ', l)
+    elif l.startswith('#'):
+        e = [int(x) for x in l.split() if x.lstrip('-').isdigit()]
+        print(f'  kernel entry -> prologue done {e[1]-e[0]} cyc; prologue done -> first step {t[0]-e[1]}; last step end -> exit {e[2]-t[-1]}; entry -> exit {e[2]-e[0]}')
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 per = 3 * L * S
