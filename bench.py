@@ -260,14 +260,19 @@ def main():
     value = world * n / (ms_per_step * 1e-3)
     launches = args.steps * eng.launch_count(n)
 
-    # ---- dominant kernel duration: one event pair per launch, mean over K launches
+    # ---- dominant kernel duration.  On the fused FC path a step IS one launch of fc_chain_kernel, so its average launch
+    # duration over the timed region is ms_total / steps (CUDA events on the launching stream, back-to-back launches).  An
+    # isolated figure (one event pair per launch, includes the event/launch gap) is reported next to it.
     durs = []
     for i in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream); step(i); b.record(stream)
         durs.append((a, b))
     torch.cuda.synchronize()
-    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in durs)
+    kernel_ms_isolated = statistics.mean(a.elapsed_time(b) for a, b in durs)
+    single_kernel_step = eng.launch_count(n) == 1
+    local_ms_per_step = ev0.elapsed_time(ev1) / args.steps
+    kernel_ms = local_ms_per_step if single_kernel_step else kernel_ms_isolated
     bytes_per_image = eng.img_bytes + 4 * C          # 256 B read + 10 x int32 written = 296 B (labels +4 B not counted)
     achieved = bytes_per_image * n / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
@@ -280,7 +285,8 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "fc_chain_kernel" if eng.active_path == _lib.PATH_TCGEN05 else "layer kernels",
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_image": bytes_per_image, "peak_source": peak_src}
+                "kernel_ms": kernel_ms, "kernel_ms_isolated_launch": kernel_ms_isolated,
+                "algorithmic_bytes_per_image": bytes_per_image, "peak_source": peak_src}
 
     # ---- sanity: the timed path is bit-exact on a sample (oracle = checker only, outside every timed region)
     parity = None

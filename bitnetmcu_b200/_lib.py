@@ -18,6 +18,7 @@ EXPORTED = [
     "bnm_model_set_option", "bnm_model_get_option", "bnm_model_active_path",
     "bnm_infer_batch", "bnm_infer_batch_device", "bnm_infer_launch_count", "bnm_host_alloc", "bnm_host_free",
     "bnm_processfclayer_batch", "bnm_relunorm_batch", "bnm_conv33relu_batch", "bnm_maxpool22_batch",
+    "bnm_quantize_images", "bnm_quantize_images_device",
 ]
 
 PATH_AUTO, PATH_LAYERS, PATH_TCGEN05 = 0, 1, 2
@@ -58,6 +59,8 @@ def load() -> C.CDLL:
         "bnm_relunorm_batch": (C.c_int, [vp, vp, vp, u32, sz]),
         "bnm_conv33relu_batch": (C.c_int, [vp, vp, u32, u32, u32, vp, sz]),
         "bnm_maxpool22_batch": (C.c_int, [vp, u32, vp, sz]),
+        "bnm_quantize_images": (C.c_int, [vp, sz, u32, vp]),
+        "bnm_quantize_images_device": (C.c_int, [vp, sz, u32, vp, vp]),
         "ReLUNorm": (u32, [vp, vp, u32]),
         "processfclayer": (None, [vp, vp, i32, u32, u32, vp]),
         "processconv33ReLU": (vp, [vp, vp, u32, u32, vp]),

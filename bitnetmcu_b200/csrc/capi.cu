@@ -559,6 +559,28 @@ extern "C" int bnm_maxpool22_batch(const int32_t *activations, uint32_t xy, int3
     return 0;
 }
 
+extern "C" int bnm_quantize_images_device(const float *images, size_t n, uint32_t elems, int8_t *out, void *stream) {
+    if (int rc = require_device()) return rc;
+    if (n == 0 || elems == 0) return 0;
+    if (!images || !out) return fail(BNM_E_ARG, "bnm_quantize_images_device: null argument");
+    launch_quantize_images(images, elems, out, n, static_cast<cudaStream_t>(stream));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail(BNM_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" int bnm_quantize_images(const float *images, size_t n, uint32_t elems, int8_t *out) {
+    if (int rc = require_device()) return rc;
+    if (n == 0 || elems == 0) return 0;
+    if (!images || !out) return fail(BNM_E_ARG, "bnm_quantize_images: null argument");
+    DevBuf in, q;
+    if (in.alloc(n * (size_t)elems * 4) || q.alloc(n * (size_t)elems)) return fail(BNM_E_CUDA, "cudaMalloc failed");
+    CU_TRY(cudaMemcpy(in.p, images, n * (size_t)elems * 4, cudaMemcpyHostToDevice));
+    launch_quantize_images(in.as<float>(), elems, q.as<int8_t>(), n, 0);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy(out, q.p, n * (size_t)elems, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // -----------------------------------------------------------------------------------------------
 // reference-named symbols (BitNetMCU_inference.h:15-60): one item, abort on failure -- never a CPU path
 // -----------------------------------------------------------------------------------------------

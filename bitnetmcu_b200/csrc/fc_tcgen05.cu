@@ -445,7 +445,10 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (kTrace && P.trace && blockIdx.x == 0 && tid == 0) P.trace[1022] = clock64();   // all roles done
-    if (kTrace && P.trace && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1025 + 2 * blockIdx.x] = (long long)gt; }
+    if (kTrace && P.trace && tid == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1025 + 2 * blockIdx.x] = (long long)gt;
+        uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.trace[1400 + blockIdx.x] = smid;
+    }
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
@@ -601,6 +604,7 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
                     e0 = std::min(e0, h[1024 + 2 * b]); e1 = std::max(e1, h[1024 + 2 * b]);
                     x0 = std::min(x0, h[1025 + 2 * b]); x1 = std::max(x1, h[1025 + 2 * b]);
                 }
+                for (unsigned b = 0; b < grid && b < 500; b++) fprintf(f, "### cta %u lifetime_ns %lld smid %lld\n", b, h[1025 + 2 * b] - h[1024 + 2 * b], h[1400 + b]);
                 fprintf(f, "## globaltimer ns: CTA entry spread %lld, first entry -> first exit %lld, first entry -> last exit %lld\n", e1 - e0, x0 - e0, x1 - e0);
             }
             fprintf(f, "## since entry: barriers %lld, loads issued %lld, tmem alloc %lld\n", h[1016] - h[1020], h[1017] - h[1020], h[1018] - h[1020]);

@@ -208,6 +208,35 @@ void launch_relunorm(const int32_t *in, uint32_t n_in, int8_t *out, uint32_t out
 }
 
 // ------------------------------------------------------------------------------------------------
+// Input quantisation, the step right before the path: test_inference.py:140-141 /
+// BitNetMCU.py:435-436:  scale = 127 / max(max|x|, 1e-5);  q = round_half_even(x * scale).clip(-128, 127)  in float32.
+// One warp per image; every operation is a single correctly rounded IEEE float32 op (no FMA contraction), so the result
+// is bit-identical to the NumPy expression.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_quantize_images(const float *__restrict__ in, uint32_t elems, int8_t *__restrict__ out, size_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t img = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (img >= n) return;
+    const float *x = in + img * elems;
+    float m = 0.0f;
+    for (uint32_t i = lane; i < elems; i += 32) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    const float scale = __fdiv_rn(127.0f, fmaxf(m, 1e-5f));
+    int8_t *q = out + img * elems;
+    for (uint32_t i = lane; i < elems; i += 32) {
+        float y = rintf(__fmul_rn(x[i], scale));            // np.round: round half to even
+        y = fminf(fmaxf(y, -128.0f), 127.0f);               // .clip(-128, 127)
+        q[i] = (int8_t)(int)y;
+    }
+}
+
+void launch_quantize_images(const float *in, uint32_t elems, int8_t *out, size_t n, cudaStream_t st) {
+    if (n == 0 || elems == 0) return;
+    k_quantize_images<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(in, elems, out, n);
+}
+
+// ------------------------------------------------------------------------------------------------
 // processconv33ReLU / processmaxpool22, one thread per output element
 // ------------------------------------------------------------------------------------------------
 __global__ void k_conv33relu(const int32_t *__restrict__ act, const int8_t *__restrict__ w, uint32_t n_w, uint32_t xy,

@@ -40,6 +40,9 @@ void launch_maxpool22(const int32_t *act, uint32_t xy, int32_t *out, size_t n, c
 bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
                          uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, cudaStream_t st);
 
+// input quantisation ahead of the path (test_inference.py:140-141): float [n][elems] -> int8 [n][elems]
+void launch_quantize_images(const float *in, uint32_t elems, int8_t *out, size_t n, cudaStream_t st);
+
 // ---- fused tcgen05 FC chain (fc_tcgen05.cu)
 struct FcChainPlan;  // opaque, owned by the model
 FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32_t in_bytes, int device, int sm_count,

@@ -142,3 +142,14 @@ def maxpool22(activations: np.ndarray, xy: int) -> np.ndarray:
     out = np.empty((a.shape[0], (xy // 2) * (xy // 2)), dtype=np.int32)
     _lib.check(lib.bnm_maxpool22_batch(_ptr(a), xy, _ptr(out), a.shape[0]), "bnm_maxpool22_batch")
     return out
+
+
+def quantize_images(images: np.ndarray) -> np.ndarray:
+    """The step right before the path (test_inference.py:140-141): float32 [n, elems] -> int8 [n, elems],
+    ``np.round(x * (127 / max(|x|.max(-1), 1e-5))).clip(-128, 127)`` computed on the GPU, bit-identical to NumPy float32."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(images, dtype=np.float32)
+    x2 = x.reshape(-1, x.shape[-1]) if x.ndim > 1 else x.reshape(1, -1)
+    out = np.empty(x2.shape, dtype=np.int8)
+    _lib.check(lib.bnm_quantize_images(_ptr(x2), x2.shape[0], x2.shape[1], _ptr(out)), "bnm_quantize_images")
+    return out

@@ -139,6 +139,15 @@ BNM_API int bnm_conv33relu_batch(const int32_t *activations, const int8_t *weigh
 /* activations int32 [n][xy*xy] -> output int32 [n][(xy/2)^2] */
 BNM_API int bnm_maxpool22_batch(const int32_t *activations, uint32_t xy_input, int32_t *output, size_t n);
 
+/* ---------------------------------------------------------------------------------------------
+ * 5. Input quantisation, the step right before the path (the reference does it in Python per image:
+ *    /root/reference/test_inference.py:140-141, BitNetMCU.py:435-436):
+ *        scale = 127 / max(max|x|, 1e-5);  q = round_half_even(x * scale) clipped to [-128, 127]      (all float32)
+ *    images float32 [n][elems] -> int8 [n][elems]; bit-identical to the NumPy expression.
+ * ------------------------------------------------------------------------------------------- */
+BNM_API int bnm_quantize_images(const float *images, size_t n, uint32_t elems, int8_t *out);                       /* host buffers */
+BNM_API int bnm_quantize_images_device(const float *images, size_t n, uint32_t elems, int8_t *out, void *stream);  /* device buffers */
+
 #ifdef __cplusplus
 }
 #endif

@@ -318,3 +318,21 @@ def test_extreme_weights_cnn(lib, oracle):
     lo_, la_ = e.infer(imgs)
     assert np.array_equal(lo_, want_logits) and np.array_equal(la_, want_labels)
     e.close()
+
+
+def test_quantize_images_matches_numpy(lib):
+    """the float -> int8 input scaling of test_inference.py:140-141, bit-identical to NumPy float32
+    (tolerance 0: every step is one correctly rounded IEEE op; np.round = round half to even)."""
+    from bitnetmcu_b200 import engine as E
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(3000, 256)).astype(np.float32)
+    x[:50] = (rng.integers(0, 256, size=(50, 256)) / 255.0 - 0.1307).astype(np.float32) / np.float32(0.3081)   # MNIST-like normalisation
+    x[50] = 0.0                                  # all-zero image: the 1e-5 floor
+    x[51] = 1e-7
+    x[52, :] = np.float32(0.5) / np.float32(127.0) * np.arange(256, dtype=np.float32)   # many exact .5 ties
+    x[53] = -x[52]
+    x[54, 0] = 3e38
+    scale = np.float32(127.0) / np.maximum(np.abs(x).max(axis=-1, keepdims=True), np.float32(1e-5))
+    want = np.round(x * scale).clip(-128, 127).astype(np.int8)
+    got = E.quantize_images(x)
+    assert got.dtype == np.int8 and np.array_equal(got, want)

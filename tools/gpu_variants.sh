@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 60 ./tools/requant_bench | grep -E "correct"; BIGROWS=1 timeout 60 ./tools/requant_bench | tee gpurun_out/requant_bench.log | grep -E "^[0-9]A|3 warps"
+timeout 60 ./tools/bin/requant_bench | grep -E "correct"; BIGROWS=1 timeout 60 ./tools/bin/requant_bench | tee gpurun_out/requant_bench.log | grep -E "^[0-9]A|3 warps"
 for lib in variants/*.so; do
   echo "== $lib"
   BNM_LIB_PATH=$PWD/$lib timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "golden_and_oracle or edge_batch or full_size" 2>&1 | tail -1

@@ -2,7 +2,9 @@ import sys, numpy as np
 lines = open(sys.argv[1]).read().splitlines()
 t = np.array([int(x) for x in lines if x and not x.startswith('#')], dtype=np.int64)
 for l in lines:
-    if l.startswith('##'):
+    if l.startswith('###'):
+        continue
+    elif l.startswith('##'):
         print(' ', l)
     elif l.startswith('#'):
         e = [int(x) for x in l.split() if x.lstrip('-').isdigit()]
@@ -20,3 +22,15 @@ for l in range(L):
         w = np.median(a[1:, l, q, 1] - a[1:, l, q, 0]); k = np.median(a[1:, l, q, 2] - a[1:, l, q, 1])
         print(f"  layer {l+1} slot {q}: wait for MMA {w:6.0f}   epilogue {k:6.0f}")
 print("  round period:", np.median(np.diff(a[:, 0, 0, 0])), "cycles for", S, "tiles per warpgroup")
+
+cta = [(int(l.split()[2]), int(l.split()[4]), int(l.split()[6])) for l in lines if l.startswith('###')]
+if cta:
+    import numpy as np
+    life = np.array([c[1] for c in cta]); sm = np.array([c[2] for c in cta]); b = np.array([c[0] for c in cta])
+    print(f"  per-CTA lifetime us: min {life.min()/1e3:.1f} median {np.median(life)/1e3:.1f} max {life.max()/1e3:.1f}")
+    n56 = b < (8192 % len(cta))
+    print(f"  56-tile CTAs: median {np.median(life[n56])/1e3:.1f}  55-tile CTAs: median {np.median(life[~n56])/1e3:.1f}")
+    order = np.argsort(life)
+    print("  slowest 12 (cta, smid, us):", [(int(b[i]), int(sm[i]), round(life[i]/1e3,1)) for i in order[-12:]])
+    print("  fastest 12 (cta, smid, us):", [(int(b[i]), int(sm[i]), round(life[i]/1e3,1)) for i in order[:12]])
+    print("  corr(lifetime, smid) =", round(float(np.corrcoef(life, sm)[0,1]),3), " corr(lifetime, smid%2) =", round(float(np.corrcoef(life, sm%2)[0,1]),3))
