@@ -183,6 +183,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "layers", "tcgen05"])
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2],
+                    help="BNM_OPT_LAUNCH_OVERLAP: 0 plain launches, 1 dependent launch (prologue overlap only), "
+                         "2 consecutive launches declared independent (the bench double-buffers inputs AND outputs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -222,12 +225,15 @@ def main():
     # ---- device-resident inputs: two buffers alternated, each (n x img_bytes = 268 MB at 1M) larger than the 126 MB L2
     host_imgs = synth_images(n, eng.img_bytes, 1234 + rank)
     d_in = [torch.from_numpy(host_imgs).to(dev), torch.from_numpy(np.ascontiguousarray(host_imgs[::-1])).to(dev)]
-    d_logits = torch.empty((n, C), dtype=torch.int32, device=dev)
-    d_labels = torch.empty(n, dtype=torch.int32, device=dev)
+    # outputs double-buffered too: step i reads d_in[i & 1] and writes d_logits[i & 1] / d_labels[i & 1], so consecutive
+    # launches touch disjoint buffers -- the promise BNM_OPT_LAUNCH_OVERLAP = 2 asks for
+    d_logits = [torch.empty((n, C), dtype=torch.int32, device=dev) for _ in range(2)]
+    d_labels = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
     stream = torch.cuda.current_stream(dev)
+    eng.set_option(_lib.OPT_LAUNCH_OVERLAP, args.overlap)
 
     def step(i):
-        eng.infer_device(d_in[i & 1], d_logits, d_labels, stream.cuda_stream)
+        eng.infer_device(d_in[i & 1], d_logits[i & 1], d_labels[i & 1], stream.cuda_stream)
 
     for i in range(args.warmup):
         step(i)
@@ -255,14 +261,17 @@ def main():
         if i % 50 == 0:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
+    # results of back-to-back (overlapped) launches, kept for the full-batch parity check below
+    snap = [(d_logits[k].cpu().numpy(), d_labels[k].cpu().numpy()) for k in range(2)]
     clocks = sampler.stop(t_wall0, time.perf_counter())
     ms_per_step = ms_total / args.steps
     value = world * n / (ms_per_step * 1e-3)
     launches = args.steps * eng.launch_count(n)
 
     # ---- dominant kernel duration.  On the fused FC path a step IS one launch of fc_chain_kernel, so its average launch
-    # duration over the timed region is ms_total / steps (CUDA events on the launching stream, back-to-back launches).  An
-    # isolated figure (one event pair per launch, includes the event/launch gap) is reported next to it.
+    # duration over the timed region is ms_total / steps (CUDA events on the launching stream, back-to-back launches; with
+    # launch overlap the ragged end of one launch runs under the start of the next, which is the point).  An isolated
+    # figure (one event pair per launch: no overlap, includes the event/launch gap) is reported next to it.
     durs = []
     for i in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,6 +326,10 @@ def main():
             ns = min(n, 1 << 16)
             oo, ol = Oracle().infer(model, host_imgs[:ns])
             parity = bool(np.array_equal(h_log[:ns], oo) and np.array_equal(h_lab[:ns], ol))
+            # ... and the device path's results from the overlapped launches, the whole batch, both buffers (buffer 1 holds
+            # the images in reverse order), against the e2e result that was just checked
+            parity = parity and bool(np.array_equal(snap[0][0], h_log) and np.array_equal(snap[0][1].view(np.uint32), h_lab)
+                                     and np.array_equal(snap[1][0], h_log[::-1]) and np.array_equal(snap[1][1].view(np.uint32), h_lab[::-1]))
         except Exception as ex:  # the checker being unavailable must not hide the measurement
             parity = f"oracle unavailable: {ex}"
         lib.bnm_host_free(p_in); lib.bnm_host_free(p_log); lib.bnm_host_free(p_lab)
@@ -336,7 +349,9 @@ def main():
             "config": {"workload": workload_name(args, model), "batch_per_gpu": n, "global_batch": n * world,
                        "parallelism": f"dp{world} (batch sharded, logits stay sharded; no data-path collective)",
                        "l2": "inputs larger than L2: two 268 MB image buffers alternated per step, TMA evict-first loads",
-                       "path": "tcgen05" if eng.active_path == _lib.PATH_TCGEN05 else "layers"},
+                       "path": "tcgen05" if eng.active_path == _lib.PATH_TCGEN05 else "layers",
+                       "launch_overlap": {0: "none", 1: "programmatic dependent launch, inputs read after the previous kernel completed",
+                                          2: "programmatic dependent launch, consecutive steps independent (inputs and outputs double-buffered)"}[args.overlap]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
             "parity_vs_oracle_sample": parity,
         }

@@ -22,7 +22,7 @@ EXPORTED = [
 ]
 
 PATH_AUTO, PATH_LAYERS, PATH_TCGEN05 = 0, 1, 2
-OPT_PATH, OPT_NF4_EXTENSION, OPT_CHUNK_IMAGES = 1, 2, 3
+OPT_PATH, OPT_NF4_EXTENSION, OPT_CHUNK_IMAGES, OPT_LAUNCH_OVERLAP = 1, 2, 3, 4
 
 
 class BnmLayer(C.Structure):

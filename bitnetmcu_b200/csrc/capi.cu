@@ -66,6 +66,7 @@ struct bnm_model {
     int opt_path = BNM_PATH_AUTO;
     int nf4_ext = 0;
     size_t chunk_images = 1 << 16;   // host pipeline chunk
+    int launch_overlap = 1;
     // fused plan
     FcChainPlan *plan = nullptr;
     std::string plan_err;
@@ -312,6 +313,12 @@ extern "C" int bnm_model_set_option(bnm_model *m, int option, int64_t value) {
         if (value < 128) return fail(BNM_E_ARG, "chunk must be >= 128 images");
         m->chunk_images = (size_t)value;
         return 0;
+    case BNM_OPT_LAUNCH_OVERLAP:
+        if (value < 0 || value > 2) return fail(BNM_E_ARG, "launch overlap mode must be 0, 1 or 2");
+        m->launch_overlap = (int)value;
+        // the CNN front-end writes the features the FC kernel reads: there the dependency is real, never declare it away
+        fc_chain_plan_set_overlap(m->plan, m->model_class == BNM_MODEL_CNNMNIST && value == 2 ? 1 : (int)value);
+        return 0;
     default:
         return fail(BNM_E_ARG, "unknown option %d", option);
     }
@@ -322,6 +329,7 @@ extern "C" int64_t bnm_model_get_option(const bnm_model *m, int option) {
     case BNM_OPT_PATH: return m->opt_path;
     case BNM_OPT_NF4_EXTENSION: return m->nf4_ext;
     case BNM_OPT_CHUNK_IMAGES: return (int64_t)m->chunk_images;
+    case BNM_OPT_LAUNCH_OVERLAP: return m->launch_overlap;
     default: return -1;
     }
 }

@@ -51,6 +51,7 @@ struct ChainParams {
     int *err;
     int32_t kadd[16];                 // argmax key offsets of the (single) logits chunk: 15-j for real classes, -2^30 for padding
     long long *trace;                 // diagnostics: clock64 per phase of CTA 0 / warpgroup 0 (null in production)
+    uint32_t wait_prior_grid;         // programmatic dependent launch: read inputs only after the previous kernel has completed
 };
 
 struct FcChainPlan {
@@ -62,6 +63,7 @@ struct FcChainPlan {
     int threads = 0;
     int sm_count = 0;
     int device = 0;
+    int overlap = 1;                  // BNM_OPT_LAUNCH_OVERLAP: 0 plain launch, 1 dependent launch + wait, 2 independent launches
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -254,6 +256,10 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
     if (kTrace && P.trace && blockIdx.x == 0 && tid == 0) P.trace[1020] = clock64();   // kernel entry
+    // Programmatic dependent launch: the next kernel in the stream may take over each SM as soon as this CTA leaves it (it
+    // cannot co-reside: shared memory and TMEM are fully used), so its launch latency and prologue -- and, when the caller
+    // declares consecutive launches independent, its first tiles -- overlap the ragged end of this one.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t n_wg = P.n_wg, n_st = P.n_stages;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -280,9 +286,9 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     };
 
     // ---------------- one-time setup
-    // One thread (lane 0 of the first issuer warp) initialises the barriers and issues the first image loads; it takes no
-    // part in staging the weights, so it never executes the generic->async proxy fence -- measured: that fence, executed by
-    // the thread that has TMA loads in flight, waits for them to land (~3 us per launch).
+    // One thread (lane 0 of the first issuer warp) initialises the barriers, starts the weight copy and issues the first image
+    // loads.  Nobody executes a generic->async proxy fence -- measured: that fence, executed by a thread that has TMA loads in
+    // flight, waits for them to land (~3 us per launch).
     if (kTrace && P.trace && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1024 + 2 * blockIdx.x] = (long long)gt; }
     const bool setup_thread = tid == n_wg * 128;
     if (setup_thread) {
@@ -292,13 +298,18 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         mbar_init(&bar_w, 1);
         fence_mbar_init();
         if (kTrace && P.trace && blockIdx.x == 0) P.trace[1016] = clock64();   // barriers initialised
-        for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
         // weight image -> smem with bulk async copies (same bytes for every CTA; L2-resident after the first wave).  The
         // async proxy writes them, so the tensor core may read them as soon as bar_w completes: no staging loop, no
-        // generic->async proxy fence in the prologue.
+        // generic->async proxy fence in the prologue.  The weights were written at model build, long before any kernel that
+        // may still be running ahead of this one, so they are fetched before the grid dependency is resolved.
         mbar_arrive_expect_tx(&bar_w, P.w_bytes);
         for (uint32_t off = 0; off < P.w_bytes; off += 32768)
             bulk_load_1d(smem + P.off_w + off, P.w_image + off, min(32768u, P.w_bytes - off), &bar_w);
+        // Everything this kernel reads or writes besides the weights may belong to the kernel launched before it: wait until
+        // that one has completed and flushed (no-op without a programmatic dependency).  Every other access of this CTA
+        // happens after a barrier that these loads complete, i.e. after this wait.
+        if (P.wait_prior_grid) asm volatile("griddepcontrol.wait;" ::: "memory");
+        for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
         if (kTrace && P.trace && blockIdx.x == 0) P.trace[1017] = clock64();   // first loads issued
     } else if (warp == 1) {
         tmem_alloc<512>(&tmem_base_s);
@@ -553,6 +564,8 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     return plan;
 }
 
+void fc_chain_plan_set_overlap(FcChainPlan *p, int mode) { if (p) p->overlap = mode; }
+
 void fc_chain_plan_destroy(FcChainPlan *p) {
     if (!p) return;
     if (p->d_w_image) cudaFree(p->d_w_image);
@@ -583,12 +596,25 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     const char *trace_path = getenv("BNM_TRACE");
     if (trace_path) { cudaMalloc(&d_trace, 2048 * sizeof(long long)); cudaMemset(d_trace, 0, 2048 * sizeof(long long)); }
     p.trace = d_trace;
+    p.wait_prior_grid = plan->overlap != 2;
     if (trace_path) {
         if (p.n_slots == 1) fc_chain_kernel<1, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
         else fc_chain_kernel<2, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
     } else {
-        if (p.n_slots == 1) fc_chain_kernel<1, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
-        else fc_chain_kernel<2, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3((unsigned)plan->threads);
+        cfg.dynamicSmemBytes = plan->smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = plan->overlap ? 1 : 0;
+        cudaError_t e = p.n_slots == 1 ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false>, tmap, p)
+                                       : cudaLaunchKernelEx(&cfg, fc_chain_kernel<2, false>, tmap, p);
+        if (e != cudaSuccess) return -4;
     }
     if (trace_path) {   // diagnostics only: synchronous dump of the phase clocks
         std::vector<long long> h(2048);

@@ -48,6 +48,8 @@ struct FcChainPlan;  // opaque, owned by the model
 FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32_t in_bytes, int device, int sm_count,
                                   char *err, size_t err_len);
 void fc_chain_plan_destroy(FcChainPlan *p);
+// 0 plain launches, 1 programmatic dependent launch (inputs read after the previous kernel completed), 2 launches declared independent
+void fc_chain_plan_set_overlap(FcChainPlan *p, int mode);
 // images int8 [n][in_bytes] (device, 16B aligned) -> logits int32 [n][n_classes], labels uint32 [n] (may be null)
 int fc_chain_launch(FcChainPlan *p, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st);
 

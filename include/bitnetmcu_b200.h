@@ -83,7 +83,14 @@ enum {
     BNM_PATH_LAYERS = 1,   /* one CUDA-core (dp4a) kernel per layer + ReLUNorm kernel; any shape          */
     BNM_PATH_TCGEN05 = 2   /* fused persistent kernel: TMA -> tcgen05.mma kind::i8 -> in-TMEM ReLUNorm     */
 };
-enum { BNM_OPT_PATH = 1, BNM_OPT_NF4_EXTENSION = 2, BNM_OPT_CHUNK_IMAGES = 3 };
+enum { BNM_OPT_PATH = 1, BNM_OPT_NF4_EXTENSION = 2, BNM_OPT_CHUNK_IMAGES = 3, BNM_OPT_LAUNCH_OVERLAP = 4 };
+/* BNM_OPT_LAUNCH_OVERLAP (fused kernel, consecutive bnm_infer_batch_device calls on one stream):
+ *   0  plain launches.
+ *   1  (default) programmatic dependent launch: the next launch's prologue runs under the tail of the previous one; inputs
+ *      are read and outputs written only after the previous kernel has completed.  Ordinary stream semantics.
+ *   2  the caller declares consecutive launches independent -- the images / logits / labels of one call are not the
+ *      buffers of the call right before it (e.g. double-buffered batches), exactly what issuing them on two streams would
+ *      promise.  The next launch's tiles then start on each SM as the previous launch leaves it. */
 
 BNM_API int bnm_version(void);
 BNM_API const char *bnm_last_error(void);           /* thread-local text of the last failure */

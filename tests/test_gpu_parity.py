@@ -177,6 +177,50 @@ def test_device_api_torch(lib, oracle):
     e.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_launch_overlap_modes(lib, oracle, mode):
+    """BNM_OPT_LAUNCH_OVERLAP: back-to-back launches on one stream stay bit-exact.  Mode 1 (dependent launch + wait) with
+    the SAME buffers reused by every launch and a producer kernel (a torch copy) feeding each launch -- ordinary stream
+    semantics must hold; mode 2 with double-buffered inputs and outputs, the promise it asks for."""
+    import torch
+    from bitnetmcu_b200 import _lib
+    m = load_model("fc")
+    n = 148 * 128 * 7 + 77                          # several tiles per SM + a ragged last tile
+    batches = [_rand_images(n, seed=20 + k) for k in range(4)]
+    want = [oracle.infer(m, b) for b in batches]
+    e = _engine("fc", 0)
+    e.set_option(_lib.OPT_LAUNCH_OVERLAP, mode)
+    s = torch.cuda.Stream()
+    src = [torch.from_numpy(b).cuda() for b in batches]
+    nbuf = 2 if mode == 2 else 1
+    d_img = [torch.empty_like(src[0]) for _ in range(nbuf)]
+    d_log = [torch.empty((n, 10), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
+    d_lab = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(nbuf)]
+    got = []
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        if mode == 2:
+            for rep in range(6):                    # inputs resident; consecutive launches use disjoint buffers
+                for k in range(4):
+                    e.infer_device(src[k], d_log[k & 1], d_lab[k & 1])
+            # the last two launches wrote batches 2 and 3 into buffers 0 and 1
+            s.synchronize()
+            got = [(d_log[0].cpu().numpy(), d_lab[0].cpu().numpy()), (d_log[1].cpu().numpy(), d_lab[1].cpu().numpy())]
+            ref = [want[2], want[3]]
+        else:
+            ref = []
+            for k in range(4):                      # producer kernel -> our kernel -> consumer kernel, same buffers every time
+                d_img[0].copy_(src[k])
+                e.infer_device(d_img[0], d_log[0], d_lab[0])
+                got.append((d_log[0].clone(), d_lab[0].clone()))
+                ref.append(want[k])
+            s.synchronize()
+            got = [(a.cpu().numpy(), b.cpu().numpy()) for a, b in got]
+    for (gl, gb), (wl, wb) in zip(got, ref):
+        assert np.array_equal(gl, wl) and np.array_equal(gb.astype(np.uint32), wb)
+    e.close()
+
+
 # ---- the four kernels one by one --------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("enc", [1, 2, 4, 12, 16, 20, 36, 64, 3])

@@ -23,7 +23,18 @@ for l in range(L):
         print(f"  layer {l+1} slot {q}: wait for MMA {w:6.0f}   epilogue {k:6.0f}")
 print("  round period:", np.median(np.diff(a[:, 0, 0, 0])), "cycles for", S, "tiles per warpgroup")
 
-cta = [(int(l.split()[2]), int(l.split()[4]), int(l.split()[6])) for l in lines if l.startswith('###')]
+iss = np.array([[int(x) for x in l.split()[2:]] for l in lines if l.startswith('#### issuer')], dtype=np.int64)
+if len(iss) >= 3 * L * S:
+    ni = len(iss) // (L * S)
+    b_ = iss[: ni * L * S].reshape(ni, L, S, 6)
+    print(f"issuer warp of warpgroup 0, {ni} rounds: median cycles per step (rounds 1..)")
+    print("    step                wait-ready  wait-tile  issue-MMA  commit  refill   step-total")
+    for l in range(L):
+        for q in range(S):
+            d = np.median(np.diff(b_[1:, l, q, :], axis=-1), axis=0)
+            print(f"    layer {l+1} slot {q}:   {d[0]:9.0f} {d[1]:10.0f} {d[2]:10.0f} {d[3]:7.0f} {d[4]:7.0f} {d.sum():10.0f}")
+    print("    issuer round period:", np.median(np.diff(b_[:, 0, 0, 0])))
+cta = [(int(l.split()[2]), int(l.split()[4]), int(l.split()[6])) for l in lines if l.startswith('### cta')]
 if cta:
     import numpy as np
     life = np.array([c[1] for c in cta]); sm = np.array([c[2] for c in cta]); b = np.array([c[0] for c in cta])
