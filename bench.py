@@ -45,10 +45,29 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def synth_images(n, img_bytes, seed):
-    """Synthetic uniform int8 images of the reference's input shape (no dataset in this sandbox)."""
+def synth_images(n, img_bytes, seed, dist="uniform"):
+    """Synthetic int8 images of the reference's input shape (no dataset in this sandbox).  SURVEY.md 8d config 2:
+    (i) "uniform" int8; (ii) "mnist": background near -20 with a blob of strokes up to 127, the value profile of
+    BitNetMCU_MNIST_test_data.h (normalised MNIST scaled to +-127) -- the GPU time must not depend on which."""
     rng = np.random.default_rng(seed)
-    return rng.integers(-128, 128, size=(n, img_bytes), dtype=np.int8)
+    if dist == "uniform":
+        return rng.integers(-128, 128, size=(n, img_bytes), dtype=np.int8)
+    side = int(round(img_bytes ** 0.5))
+    out = np.full((n, side, side), -20, dtype=np.int8)
+    if side * side != img_bytes:
+        return rng.integers(-128, 128, size=(n, img_bytes), dtype=np.int8)
+    chunk = 1 << 16
+    yy, xx = np.mgrid[0:side, 0:side].astype(np.float32)
+    for b in range(0, n, chunk):
+        m = min(chunk, n - b)
+        cy, cx = rng.uniform(5, side - 5, (2, m, 1, 1)).astype(np.float32)
+        ang = rng.uniform(0, np.pi, (m, 1, 1)).astype(np.float32)
+        # a thick stroke through (cy, cx) at angle ang: distance to the line, faded at the ends
+        d = np.abs((yy - cy) * np.cos(ang) - (xx - cx) * np.sin(ang))
+        along = np.abs((yy - cy) * np.sin(ang) + (xx - cx) * np.cos(ang))
+        ink = np.clip(1.6 - d, 0, 1) * np.clip(5.5 - along, 0, 1)
+        out[b:b + m] = np.clip(-20 + 147 * ink + rng.integers(-2, 3, size=ink.shape), -128, 127).astype(np.int8)
+    return out.reshape(n, img_bytes)
 
 
 class ClockSampler:
@@ -160,7 +179,7 @@ def run_reference_arm(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "vs_baseline": None, "dtype": "int8", "data": "synthetic" if args.dist == "uniform" else "synthetic (MNIST-like value profile)",
         "config": {"workload": workload_name(args, model), "batch_per_gpu": args.batch, "sample_per_step": n},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,6 +202,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "layers", "tcgen05"])
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "mnist"], help="synthetic image distribution (SURVEY.md 8d config 2)")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2],
                     help="BNM_OPT_LAUNCH_OVERLAP: 0 plain launches, 1 dependent launch (prologue overlap only), "
                          "2 consecutive launches declared independent (the bench double-buffers inputs AND outputs)")
@@ -223,7 +243,7 @@ def main():
     C = eng.n_classes
 
     # ---- device-resident inputs: two buffers alternated, each (n x img_bytes = 268 MB at 1M) larger than the 126 MB L2
-    host_imgs = synth_images(n, eng.img_bytes, 1234 + rank)
+    host_imgs = synth_images(n, eng.img_bytes, 1234 + rank, args.dist)
     d_in = [torch.from_numpy(host_imgs).to(dev), torch.from_numpy(np.ascontiguousarray(host_imgs[::-1])).to(dev)]
     # outputs double-buffered too: step i reads d_in[i & 1] and writes d_logits[i & 1] / d_labels[i & 1], so consecutive
     # launches touch disjoint buffers -- the promise BNM_OPT_LAUNCH_OVERLAP = 2 asks for
@@ -334,6 +354,30 @@ def main():
             parity = f"oracle unavailable: {ex}"
         lib.bnm_host_free(p_in); lib.bnm_host_free(p_log); lib.bnm_host_free(p_lab)
 
+    # ---- N > 1: the optional result exchange, timed separately -- `value` keeps the logits sharded.  A GPU
+    # ingests <= ~900 GB/s over NVLink, so gathering all logits onto every rank caps the box near 22 G images/s whatever
+    # the kernels do; labels (4 B/image) are the exchange that scales.
+    gather = None
+    if world > 1:
+        all_lab = torch.empty(n * world, dtype=torch.int32, device=dev)
+        all_log = torch.empty((n * world, C), dtype=torch.int32, device=dev)
+        def timed(fn, reps=5):
+            fn(); barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream); barrier()
+            return max_over_ranks(a.elapsed_time(b) / reps)
+        lab_ms = timed(lambda: tdist.all_gather_into_tensor(all_lab, d_labels[0]))
+        log_ms = timed(lambda: tdist.all_gather_into_tensor(all_log, d_logits[0]))
+        ok = bool(torch.equal(all_lab[rank * n:(rank + 1) * n], d_labels[0]) and torch.equal(all_log[rank * n:(rank + 1) * n], d_logits[0]))
+        gather = {"all_gather_labels_ms": lab_ms, "all_gather_logits_ms": log_ms, "backend": "nccl", "own_shard_intact": ok,
+                  "value_with_label_all_gather": world * n / ((ms_per_step + lab_ms) * 1e-3),
+                  "value_with_logits_all_gather": world * n / ((ms_per_step + log_ms) * 1e-3),
+                  "note": "serial compute + exchange per step; the headline value leaves results sharded in each GPU's HBM"}
+        del all_lab, all_log
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -345,7 +389,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8", "data": "synthetic",
+            "dtype": "int8", "data": "synthetic" if args.dist == "uniform" else "synthetic (MNIST-like value profile)",
             "config": {"workload": workload_name(args, model), "batch_per_gpu": n, "global_batch": n * world,
                        "parallelism": f"dp{world} (batch sharded, logits stay sharded; no data-path collective)",
                        "l2": "inputs larger than L2: two 268 MB image buffers alternated per step, TMA evict-first loads",
@@ -353,7 +397,7 @@ def main():
                        "launch_overlap": {0: "none", 1: "programmatic dependent launch, inputs read after the previous kernel completed",
                                           2: "programmatic dependent launch, consecutive steps independent (inputs and outputs double-buffered)"}[args.overlap]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
-            "parity_vs_oracle_sample": parity,
+            "parity_vs_oracle_sample": parity, "gather": gather,
         }
         print(json.dumps(out))
     eng.close()
