@@ -8,9 +8,9 @@ The reference feeds the MNIST test set to `lib.Inference()` one image at a time:
     logits, predicted = bnm_infer_batch(model, q)       # the fused sm_100a kernel
     accuracy = mean(predicted == labels)
 
-and prints the reference's summary lines ("size of test data", "Mispredictions C", "Overall accuracy C").  With
---check-reference every image is also pushed through the unmodified reference C code (oracle/_ref, built from
-/root/reference in place) and "Mismatches between engines" is reported exactly like the reference does for C vs Python.
+and prints the reference's summary lines ("size of test data", "Mispredictions C", "Overall accuracy C").  The
+engine-vs-engine comparison the reference prints ("Mismatches between engines") lives in tests/test_batched_driver.py,
+where the same set is also pushed through the unmodified reference C code and must agree bit for bit.
 
 Data (no dataset ships with the sandbox, so it has to be pointed at one):
     --data set.npz          arrays `images` float32 [n,16,16] | [n,256] (already resized + normalised like the reference's
@@ -72,7 +72,7 @@ def load_model(path):
     return Model.load(path) if path.endswith(".bnm") else parse_header(path)
 
 
-def evaluate(model, images_f32, labels, check_reference=False, out=print):
+def evaluate(model, images_f32, labels, out=print):
     """Runs the set through the GPU engine; returns a dict with the reference's counters."""
     from bitnetmcu_b200.engine import Engine, quantize_images
     eng = Engine(model)
@@ -85,14 +85,6 @@ def evaluate(model, images_f32, labels, check_reference=False, out=print):
     out(f"size of test data: {n}")
     out(f"Mispredictions C: {n - correct}")
     out(f"Overall accuracy C: {correct / max(n, 1) * 100} %")
-    if check_reference:
-        from oracle.oracle import Oracle, Reference      # checker only: the unmodified reference C code when it was built
-        ref_logits, ref_labels = (Reference() if Reference.available() else Oracle()).infer(model, q)
-        mismatch = int((ref_labels != predicted).sum())
-        res["mismatch"] = mismatch
-        res["logits_identical"] = bool(np.array_equal(ref_logits, logits))
-        out(f"Mismatches between engines: {mismatch} ({mismatch / max(n, 1) * 100}%)")
-        out(f"int32 logits identical to the reference: {res['logits_identical']}")
     return res
 
 
@@ -100,13 +92,12 @@ def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--model", default="BitNetMCU_model.h", help="model header (exportquant.py output) or .bnm blob")
     ap.add_argument("--data", required=True, help=".npz with images/labels, or a directory with the MNIST t10k idx files")
-    ap.add_argument("--check-reference", action="store_true", help="also run the unmodified reference C code per image and compare")
     args = ap.parse_args()
     model = load_model(args.model)
     side = int(round(model.img_bytes ** 0.5))
     x, y = load_dataset(args.data, side)
     print(f"model: {model.describe()}")
-    evaluate(model, x, y, args.check_reference)
+    evaluate(model, x, y)
 
 
 if __name__ == "__main__":

@@ -66,8 +66,12 @@ def test_batched_evaluation_matches_reference(which):
     model = Model.load(os.path.join(GOLD, "models", which + ".bnm"))
     x, labels, digits = _float_set(40)
     lines = []
-    res = d.evaluate(model, x, labels, check_reference=True, out=lines.append)
+    res = d.evaluate(model, x, labels, out=lines.append)
     assert np.array_equal(res["quantized"], digits)
+    # "Mismatches between engines" (test_inference.py:166-175): the unmodified reference C code on the same int8 images
+    from oracle.oracle import Oracle, Reference
+    ref_logits, ref_labels = (Reference() if Reference.available() else Oracle()).infer(model, res["quantized"])
+    assert np.array_equal(ref_labels, res["predicted"]) and np.array_equal(ref_logits, res["logits"])
     # the reference scores 10/10 on its own test digits with both shipped models (BitNetMCU_MNIST_test.c)
-    assert res["n"] == 400 and res["correct_c"] == 400 and res["mismatch"] == 0 and res["logits_identical"]
+    assert res["n"] == 400 and res["correct_c"] == 400
     assert lines[0] == "size of test data: 400" and lines[1] == "Mispredictions C: 0" and lines[2] == "Overall accuracy C: 100.0 %"
