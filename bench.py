@@ -217,8 +217,9 @@ def main():
 
     rank, local_rank, world = bdist.env_rank_world()
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...", printed at NCCL_DEBUG=VERSION/INFO) off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("BNM_NCCL_DEBUG", "WARN")
+        # stdout carries exactly one JSON line: NCCL writes its banner ("NCCL version ...", any NCCL_DEBUG level from VERSION
+        # up, WARN included) and its INFO log to stdout unless told otherwise -- send them to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         bdist.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
