@@ -165,7 +165,7 @@ def run_reference_arm(args):
     except Exception:
         pass
     model = load_model(args.model)
-    images = synth_images(args.batch, model.img_bytes, 1234)
+    images = synth_images(args.batch, model.img_bytes, 1234, args.dist)
     base, impl, n, threads = cpu_reference_rate(model, images, budget_s=1.0, reps=1)
     for _ in range(args.warmup):
         impl.infer(model, images[:n], threads=threads)
@@ -184,14 +184,28 @@ def run_reference_arm(args):
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=RESULT_OUT, flush=True)
 
 
 def workload_name(args, model):
     return f"{args.model}: {model.describe()} | batch {args.batch} x {model.img_bytes} B int8 per GPU"
 
 
+RESULT_OUT = sys.stdout
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries loaded later write to file descriptor 1 behind Python's back
+    (NCCL prints its "NCCL version ..." banner there at NCCL_DEBUG=VERSION/WARN), so keep a private copy of the real
+    stdout for the result and point descriptor 1 at stderr for everything else."""
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -217,9 +231,7 @@ def main():
 
     rank, local_rank, world = bdist.env_rank_world()
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL writes its banner ("NCCL version ...", any NCCL_DEBUG level from VERSION
-        # up, WARN included) and its INFO log to stdout unless told otherwise -- send them to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's INFO log: stderr, not stdout (see claim_stdout)
         bdist.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -400,7 +412,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
             "parity_vs_oracle_sample": parity, "gather": gather,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=RESULT_OUT, flush=True)
     eng.close()
     if world > 1:
         tdist.destroy_process_group()
