@@ -93,6 +93,11 @@ static void free_fc_dev(bnm_model *m) {
     m->plan = nullptr;
 }
 
+static int effective_overlap(const bnm_model *m) {
+    // the CNN front-end writes the features the FC kernel reads: there the dependency is real, never declare it away
+    return m->model_class == BNM_MODEL_CNNMNIST && m->launch_overlap == 2 ? 1 : m->launch_overlap;
+}
+
 // decode all FC layers into int8 planes and (re)build the fused plan
 static int build_fc_dev(bnm_model *m) {
     free_fc_dev(m);
@@ -108,15 +113,23 @@ static int build_fc_dev(bnm_model *m) {
         L.k_pad = round_up(H.n_in, 32);
         L.n_pad = round_up(H.n_out, 16);
         size_t plane = (size_t)L.k_pad * L.n_pad;
-        CU_TRY(cudaMalloc(&L.dense_a, plane));
-        CU_TRY(cudaMalloc(&L.dense_b, plane));
-        CU_TRY(cudaMalloc(&L.quad_a, plane));
-        CU_TRY(cudaMalloc(&L.quad_b, plane));
-        CU_TRY(cudaMemset(d_flag, 0, sizeof(int)));
-        launch_decode_fc(H.d_packed, H.enc, H.n_in, H.n_out, L.k_pad, L.n_pad, L.dense_a, L.dense_b, L.quad_a, L.quad_b,
-                         m->nf4_ext, d_flag, 0);
         int flag = 0;
-        CU_TRY(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        cudaError_t e = cudaMalloc(&L.dense_a, plane);
+        if (e == cudaSuccess) e = cudaMalloc(&L.dense_b, plane);
+        if (e == cudaSuccess) e = cudaMalloc(&L.quad_a, plane);
+        if (e == cudaSuccess) e = cudaMalloc(&L.quad_b, plane);
+        if (e == cudaSuccess) e = cudaMemset(d_flag, 0, sizeof(int));
+        if (e == cudaSuccess) {
+            launch_decode_fc(H.d_packed, H.enc, H.n_in, H.n_out, L.k_pad, L.n_pad, L.dense_a, L.dense_b, L.quad_a, L.quad_b,
+                             m->nf4_ext, d_flag, 0);
+            e = cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+        }
+        if (e != cudaSuccess) {   // nothing half-built stays behind
+            cudaFree(L.dense_a); cudaFree(L.dense_b); cudaFree(L.quad_a); cudaFree(L.quad_b);
+            cudaFree(d_flag);
+            free_fc_dev(m);
+            return fail(BNM_E_CUDA, "weight decode of an FC layer failed: %s", cudaGetErrorString(e));
+        }
         if (!flag) {   // no residual plane needed (everything but FP130 layers that contain +128)
             cudaFree(L.dense_b);
             cudaFree(L.quad_b);
@@ -134,6 +147,7 @@ static int build_fc_dev(bnm_model *m) {
     uint32_t in_bytes = m->model_class == BNM_MODEL_CNNMNIST ? m->feat_stride : m->img_bytes;
     m->plan = fc_chain_plan_create(m->fc.data(), (int)m->fc.size(), in_bytes, m->device, m->sm_count, err, sizeof(err));
     m->plan_err = err;
+    fc_chain_plan_set_overlap(m->plan, effective_overlap(m));
     // scratch must be re-sized for the new widths
     m->scratch_n = 0;
     return 0;
@@ -316,8 +330,7 @@ extern "C" int bnm_model_set_option(bnm_model *m, int option, int64_t value) {
     case BNM_OPT_LAUNCH_OVERLAP:
         if (value < 0 || value > 2) return fail(BNM_E_ARG, "launch overlap mode must be 0, 1 or 2");
         m->launch_overlap = (int)value;
-        // the CNN front-end writes the features the FC kernel reads: there the dependency is real, never declare it away
-        fc_chain_plan_set_overlap(m->plan, m->model_class == BNM_MODEL_CNNMNIST && value == 2 ? 1 : (int)value);
+        fc_chain_plan_set_overlap(m->plan, effective_overlap(m));
         return 0;
     default:
         return fail(BNM_E_ARG, "unknown option %d", option);

@@ -153,3 +153,16 @@ def quantize_images(images: np.ndarray) -> np.ndarray:
     out = np.empty(x2.shape, dtype=np.int8)
     _lib.check(lib.bnm_quantize_images(_ptr(x2), x2.shape[0], x2.shape[1], _ptr(out)), "bnm_quantize_images")
     return out
+
+
+def quantize_images_device(images, out, stream: Optional[int] = None) -> None:
+    """Device-buffer form: images torch.float32 [n, elems] -> out torch.int8 [n, elems] on the same GPU, asynchronous on
+    ``stream`` (default: torch's current stream), so it chains with ``Engine.infer_device`` without a host pass."""
+    import torch
+    lib = _lib.load()
+    assert images.is_contiguous() and out.is_contiguous() and images.dtype == torch.float32 and out.dtype == torch.int8
+    assert images.dim() == 2 and tuple(out.shape) == tuple(images.shape)
+    if stream is None:
+        stream = torch.cuda.current_stream(images.device).cuda_stream
+    _lib.check(lib.bnm_quantize_images_device(C.c_void_p(images.data_ptr()), images.shape[0], images.shape[1],
+                                              C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "bnm_quantize_images_device")

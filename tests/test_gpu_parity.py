@@ -380,3 +380,29 @@ def test_quantize_images_matches_numpy(lib):
     want = np.round(x * scale).clip(-128, 127).astype(np.int8)
     got = E.quantize_images(x)
     assert got.dtype == np.int8 and np.array_equal(got, want)
+
+
+def test_float_images_to_labels_on_device(lib, oracle):
+    """float images -> bnm_quantize_images_device -> bnm_infer_batch_device on one stream, nothing touches the host in
+    between; compared with the NumPy scaling (test_inference.py:140-141) followed by the oracle."""
+    import torch
+    from bitnetmcu_b200 import engine as E
+    m = load_model("fc")
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(5000, 256)).astype(np.float32)
+    scale = np.float32(127.0) / np.maximum(np.abs(x).max(axis=-1, keepdims=True), np.float32(1e-5))
+    q = np.round(x * scale).clip(-128, 127).astype(np.int8)
+    want_logits, want_labels = oracle.infer(m, q)
+    e = _engine("fc", 0)
+    d_x = torch.from_numpy(x).cuda()
+    d_q = torch.empty((5000, 256), dtype=torch.int8, device="cuda")
+    d_log = torch.empty((5000, 10), dtype=torch.int32, device="cuda")
+    d_lab = torch.empty(5000, dtype=torch.int32, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        E.quantize_images_device(d_x, d_q)
+        e.infer_device(d_q, d_log, d_lab)
+    s.synchronize()
+    assert np.array_equal(d_q.cpu().numpy(), q)
+    assert np.array_equal(d_log.cpu().numpy(), want_logits) and np.array_equal(d_lab.cpu().numpy().astype(np.uint32), want_labels)
+    e.close()
