@@ -217,9 +217,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "layers", "tcgen05"])
     ap.add_argument("--dist", default="uniform", choices=["uniform", "mnist"], help="synthetic image distribution (SURVEY.md 8d config 2)")
-    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2],
+    ap.add_argument("--overlap", type=int, default=2, choices=[0, 1, 2],
                     help="BNM_OPT_LAUNCH_OVERLAP: 0 plain launches, 1 dependent launch (prologue overlap only), "
-                         "2 consecutive launches declared independent (the bench double-buffers inputs AND outputs)")
+                         "2 consecutive launches declared independent (the bench double-buffers inputs AND outputs); "
+                         "the plain-launch figure is always reported next to the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -312,6 +313,21 @@ def main():
         durs.append((a, b))
     torch.cuda.synchronize()
     kernel_ms_isolated = statistics.mean(a.elapsed_time(b) for a, b in durs)
+    # ---- the same K steps with plain launches (BNM_OPT_LAUNCH_OVERLAP = 0), for reference next to the headline
+    plain_ms = None
+    if args.overlap != 0:
+        eng.set_option(_lib.OPT_LAUNCH_OVERLAP, 0)
+        for i in range(3):
+            step(i)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        p1.record(stream)
+        barrier()
+        plain_ms = max_over_ranks(p0.elapsed_time(p1)) / args.steps
+        eng.set_option(_lib.OPT_LAUNCH_OVERLAP, args.overlap)
     single_kernel_step = eng.launch_count(n) == 1
     local_ms_per_step = ev0.elapsed_time(ev1) / args.steps
     kernel_ms = local_ms_per_step if single_kernel_step else kernel_ms_isolated
@@ -328,6 +344,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "fc_chain_kernel" if eng.active_path == _lib.PATH_TCGEN05 else "layer kernels",
                 "kernel_ms": kernel_ms, "kernel_ms_isolated_launch": kernel_ms_isolated,
+                "kernel_ms_plain_launches": plain_ms,
+                "frac_plain_launches": (bytes_per_image * n / (plain_ms * 1e-3) / 1e9 / peak) if (plain_ms and single_kernel_step) else None,
                 "algorithmic_bytes_per_image": bytes_per_image, "peak_source": peak_src}
 
     # ---- sanity: the timed path is bit-exact on a sample (oracle = checker only, outside every timed region)
@@ -411,6 +429,7 @@ def main():
                                           2: "programmatic dependent launch, consecutive steps independent (inputs and outputs double-buffered)"}[args.overlap]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
             "parity_vs_oracle_sample": parity, "gather": gather,
+            "value_plain_launches": (world * n / (plain_ms * 1e-3)) if plain_ms else None,
         }
         print(json.dumps(out), file=RESULT_OUT, flush=True)
     eng.close()

@@ -66,7 +66,7 @@ struct bnm_model {
     int opt_path = BNM_PATH_AUTO;
     int nf4_ext = 0;
     size_t chunk_images = 1 << 16;   // host pipeline chunk
-    int launch_overlap = 1;
+    int launch_overlap = 0;
     // fused plan
     FcChainPlan *plan = nullptr;
     std::string plan_err;

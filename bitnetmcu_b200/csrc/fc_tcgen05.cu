@@ -51,7 +51,9 @@ struct ChainParams {
     int *err;
     int32_t kadd[16];                 // argmax key offsets of the (single) logits chunk: 15-j for real classes, -2^30 for padding
     long long *trace;                 // diagnostics: clock64 per phase of CTA 0 / warpgroup 0 (null in production)
+    uint32_t stagger_cycles;          // tuning knob (BNM_STAGGER_NS): warpgroup g starts no earlier than g * this after kernel entry
     uint32_t wait_prior_grid;         // programmatic dependent launch: read inputs only after the previous kernel has completed
+    uint32_t early_trigger;           // let the next launch's CTAs take over SMs as this launch's CTAs leave (full grids only)
 };
 
 struct FcChainPlan {
@@ -63,7 +65,7 @@ struct FcChainPlan {
     int threads = 0;
     int sm_count = 0;
     int device = 0;
-    int overlap = 1;                  // BNM_OPT_LAUNCH_OVERLAP: 0 plain launch, 1 dependent launch + wait, 2 independent launches
+    int overlap = 0;                  // BNM_OPT_LAUNCH_OVERLAP: 0 plain launch, 1 dependent launch + wait, 2 independent launches
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -253,13 +255,17 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bar_w;   // weight image landed (one bulk async copy, no generic-proxy writes)
 
+    const long long t_entry = clock64();
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
     if (kTrace && P.trace && blockIdx.x == 0 && tid == 0) P.trace[1020] = clock64();   // kernel entry
     // Programmatic dependent launch: the next kernel in the stream may take over each SM as soon as this CTA leaves it (it
     // cannot co-reside: shared memory and TMEM are fully used), so its launch latency and prologue -- and, when the caller
     // declares consecutive launches independent, its first tiles -- overlap the ragged end of this one.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Only when the grid fills the GPU (one CTA per SM): then launch k+1 can start no CTA before the matching CTA of launch k
+    // has left, and launch k+2 none before all of launch k are gone -- at most two consecutive launches ever overlap.  A
+    // smaller grid leaves SMs free, where later launches could pile up next to earlier ones; it triggers at completion.
+    if (P.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t n_wg = P.n_wg, n_st = P.n_stages;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -295,6 +301,9 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     if (kTrace && P.trace && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1024 + 2 * blockIdx.x] = (long long)gt; }
     const bool setup_thread = tid == n_wg * 128;
     if (setup_thread) {
+#ifdef BNM_PREFETCH_TMAP
+        tma_prefetch_desc(&tmap_in);   // the descriptor fetch (first TMA use) overlaps the barrier setup
+#endif
         for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[0][s], 1); mbar_init(&bar_full[1][s], 1); }
         for (uint32_t g = 0; g < n_wg; g++)
             for (int q = 0; q < kSlots; q++) { mbar_init(&bar_mma[g][q], 1); mbar_init(&bar_ready[g][q], kReadyArrivals); }
@@ -312,7 +321,17 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         // that one has completed and flushed (no-op without a programmatic dependency).  Every other access of this CTA
         // happens after a barrier that these loads complete, i.e. after this wait.
         if (P.wait_prior_grid) asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef BNM_LOAD_ORDER
+        // first tile of every warpgroup before the second ones: the warpgroups start 1 tile-arrival apart instead of 2
+        for (uint32_t q = 0; q < (uint32_t)kSlots; q++)
+            for (uint32_t g = 0; g < n_wg; g++) {
+                const uint32_t i = g * kSlots + q;
+                if (i < n_st && i < my_tiles) issue_tile_load(i);
+            }
+        for (uint32_t i = n_virt; i < n_st && i < my_tiles; i++) issue_tile_load(i);
+#else
         for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
+#endif
         if (kTrace && P.trace && blockIdx.x == 0) P.trace[1017] = clock64();   // first loads issued
     } else if (warp == 1) {
         tmem_alloc<512>(&tmem_base_s);
@@ -330,11 +349,20 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         const bool leader = elect_one();
         uint32_t ready_phase = 0;   // one phase bit per slot
         mbar_wait(&bar_w, 0, P.err, 6);   // weight tiles are in shared memory
+        if (P.stagger_cycles) {   // keep the warpgroups out of phase (they would otherwise compete for the ALU pipe in lockstep)
+            const long long t_go = t_entry + (long long)g * P.stagger_cycles;
+            while (clock64() < t_go) __nanosleep(64);
+        }
         for (uint32_t r = 0; r < n_rounds; r++)
             for (int l = 0; l < P.n_layers; l++)
 #pragma unroll 1
                 for (int q = 0; q < kSlots; q++) {
-                    const uint32_t v = g * kSlots + q, i = r * n_virt + v;
+                    const uint32_t v = g * kSlots + q;
+#ifdef BNM_TILE_INTERLEAVE
+                    const uint32_t i = r * n_virt + q * n_wg + g;
+#else
+                    const uint32_t i = r * n_virt + v;
+#endif
                     if (i >= my_tiles) continue;
                     const uint32_t d_tmem = tmem_base + v * P.tmem_wg_cols, a_tmem = d_tmem + P.tmem_a_off;
                     if (r != 0 || l != 0) {   // previous epilogue step of this slot: A written / D drained by all 4 warps
@@ -368,12 +396,17 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         uint32_t trace_n = 0;
 #define BNM_TRACE_POINT() do { if (kTrace && tracing && trace_n < 1000) P.trace[trace_n++] = clock64(); } while (0)
 
-        for (uint32_t r = 0, i0 = g * kSlots; r < n_rounds; r++, i0 += n_virt)
+        #ifdef BNM_TILE_INTERLEAVE
+        const uint32_t i_first = g, i_slot = n_wg;
+#else
+        const uint32_t i_first = g * kSlots, i_slot = 1;
+#endif
+        for (uint32_t r = 0, i0 = i_first; r < n_rounds; r++, i0 += n_virt)
             for (int l = 0; l < n_layers; l++) {
                 const uint32_t n_pad_l = P.n_pad[l];
 #pragma unroll 1
                 for (int q = 0; q < kSlots; q++) {
-                    const uint32_t i = i0 + q;
+                    const uint32_t i = i0 + q * i_slot;
                     if (i >= my_tiles) continue;
                     const uint32_t d_tm = d_tm0 + q * slot_cols;
                     BNM_TRACE_POINT();   // step start
@@ -567,7 +600,15 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     return plan;
 }
 
-void fc_chain_plan_set_overlap(FcChainPlan *p, int mode) { if (p) p->overlap = mode; }
+void fc_chain_plan_set_overlap(FcChainPlan *p, int mode) {
+    if (!p) return;
+    p->overlap = mode;
+    // Overlapped launches find HBM uncongested, all six first tiles of a CTA land within ~1 us and the three warpgroups
+    // would run in lockstep, competing for the ALU pipe at the same moments (measured -3 %).  Start warpgroup g no earlier
+    // than g x 2 us after kernel entry (a third of the ~6 us round).  Plain launches get the same offsets for free from
+    // the start-up burst (tile i of an SM arrives ~0.8 us after tile i-1), there the delay only costs ramp time.
+    p->p.stagger_cycles = mode == 2 ? 3600 : 0;
+}
 
 void fc_chain_plan_destroy(FcChainPlan *p) {
     if (!p) return;
@@ -600,6 +641,8 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     if (trace_path) { cudaMalloc(&d_trace, 2048 * sizeof(long long)); cudaMemset(d_trace, 0, 2048 * sizeof(long long)); }
     p.trace = d_trace;
     p.wait_prior_grid = plan->overlap != 2;
+    p.early_trigger = plan->overlap != 0 && grid == (unsigned)plan->sm_count;
+    if (const char *e = getenv("BNM_STAGGER_NS")) p.stagger_cycles = (uint32_t)(atof(e) * 1.8);   // tuning knob; ~1.8 cycles per ns under load
     if (trace_path) {
         if (p.n_slots == 1) fc_chain_kernel<1, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
         else fc_chain_kernel<2, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);

@@ -85,13 +85,16 @@ enum {
 };
 enum { BNM_OPT_PATH = 1, BNM_OPT_NF4_EXTENSION = 2, BNM_OPT_CHUNK_IMAGES = 3, BNM_OPT_LAUNCH_OVERLAP = 4 };
 /* BNM_OPT_LAUNCH_OVERLAP (fused kernel, consecutive bnm_infer_batch_device calls on one stream):
- *   0  plain launches.
- *   1  (default) programmatic dependent launch: the next launch's prologue runs under the tail of the previous one; inputs
- *      are read and outputs written only after the previous kernel has completed.  Ordinary stream semantics.
+ *   0  (default) plain launches, ordinary stream semantics.
+ *   1  programmatic dependent launch with a grid-dependency wait: the next launch's prologue (barriers, TMEM, weights) runs
+ *      under the tail of the previous one; inputs are read and outputs written only after the previous kernel has
+ *      completed.  Ordinary stream semantics.  Measured erratic on B200 (-2 % ... +7 % against mode 0 for builds that
+ *      differ in one instruction), hence not the default.
  *   2  the caller declares consecutive launches independent -- the images / logits / labels of one call are not the
  *      buffers of the call right before it (e.g. double-buffered batches), exactly what issuing them on two streams would
- *      promise.  The next launch's tiles then start on each SM as the previous launch leaves it. */
-
+ *      promise.  The next launch's tiles then start on each SM as the previous launch leaves it (-6 ... -9 % per step).
+ *      Only launches that fill the GPU (>= one 128-image tile per SM) trigger early: at most two consecutive launches are
+ *      ever in flight together.  CNN models are held at mode 1 (the front-end kernel really feeds the FC kernel). */
 BNM_API int bnm_version(void);
 BNM_API const char *bnm_last_error(void);           /* thread-local text of the last failure */
 BNM_API int bnm_device_count(void);                 /* 0 when no CUDA device is usable        */
