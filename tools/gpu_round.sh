@@ -13,5 +13,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fc_c
 fi
 ls -la gpurun_out | head -30
 echo "== batch 4M (ramp/tail amortised)"
-timeout 300 python bench.py --batch 4194304 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | cut -c1-260 | tee gpurun_out/bench_4m.json
+timeout 300 python bench.py --batch 4194304 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | tee gpurun_out/bench_4m.json | cut -c1-260
 ./tools/gpu_models.sh

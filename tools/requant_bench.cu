@@ -30,6 +30,23 @@ __device__ __forceinline__ uint32_t packA(uint32_t x0, uint32_t x1, uint32_t x2,
     uint32_t lo = __byte_perm(z0, z1, 0x0073), hi = __byte_perm(z2, z3, 0x0073);
     return __byte_perm(lo, hi, 0x5410);
 }
+// C : clamp(x + r, 0, cap) * mult  ==  min(max(x, 0), cap - r) * mult + r * mult : the rounding add moves into the IMAD's
+//     addend and the clamp becomes a 2-input VIMNMX.RELU (full rate) instead of the 3-input VIADDMNMX.RELU (half rate)
+__device__ __forceinline__ uint32_t packC(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, int capr, uint32_t mult, uint32_t radd) {
+    uint32_t z0, z1, z2, z3;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(z0) : "r"((uint32_t)__vimin_s32_relu((int)x0, capr)), "r"(mult), "r"(radd));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(z1) : "r"((uint32_t)__vimin_s32_relu((int)x1, capr)), "r"(mult), "r"(radd));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(z2) : "r"((uint32_t)__vimin_s32_relu((int)x2, capr)), "r"(mult), "r"(radd));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(z3) : "r"((uint32_t)__vimin_s32_relu((int)x3, capr)), "r"(mult), "r"(radd));
+    uint32_t lo = __byte_perm(z0, z1, 0x0073), hi = __byte_perm(z2, z3, 0x0073);
+    return __byte_perm(lo, hi, 0x5410);
+}
+__device__ __forceinline__ int max16_2in(const uint32_t *v, int m) {   // 2-input VIMNMX chains (full rate)
+    int m2 = 0, m3 = 0, m4 = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) { m = max(m, (int)v[j]); m2 = max(m2, (int)v[j + 1]); m3 = max(m3, (int)v[j + 2]); m4 = max(m4, (int)v[j + 3]); }
+    return max(max(m, m2), max(m3, m4));
+}
 __device__ __forceinline__ int hiB(uint32_t x, const Coef &c) {
     int d;   // t = (x >> (s-1)) - 127 = hi32(x * 2^(33-s)) - 127: ONE IMAD.HI (FMA pipe)
     asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(d) : "r"((int)x), "r"(c.mw), "r"(-127));
@@ -58,9 +75,14 @@ template <int NB> __global__ void k(const int *in, uint32_t *out, long long *cyc
     for (int it = 0; it < iters; it++) {
         int mc[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) mc[c] = max16(v + 16 * c, 0);
-        Coef k = coef(max(__vimax3_s32(mc[0], mc[1], mc[2]), mc[3]));
-        if (NB > 0 && __all_sync(0xffffffffu, k.shift >= 3)) {
+        for (int c = 0; c < 4; c++) mc[c] = NB >= 6 ? max16_2in(v + 16 * c, 0) : max16(v + 16 * c, 0);
+        Coef k = coef(NB >= 6 ? max(max(mc[0], mc[1]), max(mc[2], mc[3])) : max(__vimax3_s32(mc[0], mc[1], mc[2]), mc[3]));
+        if (NB >= 5) {
+            const int capr = k.cap - k.rounding;
+            const uint32_t radd = (uint32_t)k.rounding * k.mult;
+#pragma unroll
+            for (int w = 0; w < 16; w++) acc[w] ^= packC(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], capr, k.mult, radd);
+        } else if (NB > 0 && __all_sync(0xffffffffu, k.shift >= 3)) {
 #pragma unroll
             for (int w = 0; w < 16; w++) {
                 uint32_t r = (w & 3) < NB ? packB(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3], k)
@@ -95,10 +117,11 @@ int main() {
     CK(cudaMalloc(&din, 256 * 64 * 4)); CK(cudaMalloc(&dout, NT * 16 * 4)); CK(cudaMalloc(&dc, 8));
     CK(cudaMemcpy(din, h, 256 * 64 * 4, cudaMemcpyHostToDevice));
     uint32_t *ho = (uint32_t *)malloc(NT * 16 * 4);
-    const char *names[5] = {"4A+0B (VIADDMNMX+IMAD+PRMT)", "3A+1B", "2A+2B", "1A+3B", "0A+4B (IMAD.HI+I2IP.S8+fix)"};
-    for (int var = 0; var < 5; var++) {
+    const char *names[7] = {"4A+0B (VIADDMNMX+IMAD+PRMT)", "3A+1B", "2A+2B", "1A+3B", "0A+4B (IMAD.HI+I2IP.S8+fix)",
+                            "C (VIMNMX.RELU+IMAD(+r*mult)+PRMT)", "C2 (C + 2-input max chains)"};
+    for (int var = 0; var < 7; var++) {
         // correctness: one iteration
-        if (var == 0) launch<0>(din, dout, dc, 256, 1); else if (var == 1) launch<1>(din, dout, dc, 256, 1); else if (var == 2) launch<2>(din, dout, dc, 256, 1); else if (var == 3) launch<3>(din, dout, dc, 256, 1); else launch<4>(din, dout, dc, 256, 1);
+        if (var == 0) launch<0>(din, dout, dc, 256, 1); else if (var == 1) launch<1>(din, dout, dc, 256, 1); else if (var == 2) launch<2>(din, dout, dc, 256, 1); else if (var == 3) launch<3>(din, dout, dc, 256, 1); else if (var == 4) launch<4>(din, dout, dc, 256, 1); else if (var == 5) launch<5>(din, dout, dc, 256, 1); else launch<6>(din, dout, dc, 256, 1);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(ho, dout, 256 * 16 * 4, cudaMemcpyDeviceToHost));
         long bad = 0;
@@ -115,7 +138,7 @@ int main() {
         printf("%-28s correctness: %ld mismatches of %d\n", names[var], bad, 256 * 64);
         for (int wps : {1, 2, 3, 4}) {
             int nt = 128 * wps;
-            if (var == 0) launch<0>(din, dout, dc, nt, 200); else if (var == 1) launch<1>(din, dout, dc, nt, 200); else if (var == 2) launch<2>(din, dout, dc, nt, 200); else if (var == 3) launch<3>(din, dout, dc, nt, 200); else launch<4>(din, dout, dc, nt, 200);
+            if (var == 0) launch<0>(din, dout, dc, nt, 200); else if (var == 1) launch<1>(din, dout, dc, nt, 200); else if (var == 2) launch<2>(din, dout, dc, nt, 200); else if (var == 3) launch<3>(din, dout, dc, nt, 200); else if (var == 4) launch<4>(din, dout, dc, nt, 200); else if (var == 5) launch<5>(din, dout, dc, nt, 200); else launch<6>(din, dout, dc, nt, 200);
             CK(cudaDeviceSynchronize());
             long long c; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
             printf("    %d warps/SMSP: %7.1f cycles per 64-accumulator epilogue per warp  -> %6.1f per SMSP-epilogue\n", wps, c / 200.0, c / 200.0 / wps);
