@@ -535,13 +535,15 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
         if (L.n_pad > 256) { delete plan; return fail("fused path: layer wider than 256 outputs"); }
         p.n_pad[l] = L.n_pad;
         p.n_real[l] = L.n_out;
-        p.k_steps[l] = l == 0 ? p.in_atoms * 4 : L.k_pad / 32;
+        // K of layer l > 0: the activations past the previous layer's (padded) width are zero -- e.g. Ternary pads n_in to a
+        // multiple of 10 with zero trits (64 -> 70, exportquant.py:132-137) -- so those K-steps are dropped, exactly
+        p.k_steps[l] = l == 0 ? p.in_atoms * 4 : round_up(std::min(L.k_pad, layers[l - 1].n_pad), 32) / 32;
         p.planes[l] = L.dense_b ? 2 : 1;
         p.b_off[l] = w_off;
         p.idesc[l] = make_idesc_i8(128, L.n_pad);
         w_off += p.planes[l] * p.k_steps[l] * L.n_pad * 32;
         d_cols = std::max(d_cols, L.n_pad);
-        if (l > 0) a_cols = std::max(a_cols, std::max(L.k_pad, layers[l - 1].n_pad) / 4);
+        if (l > 0) a_cols = std::max(a_cols, std::max(p.k_steps[l] * 32, layers[l - 1].n_pad) / 4);
     }
     p.w_bytes = w_off;
     p.n_classes = layers[n_layers - 1].n_out;
