@@ -295,20 +295,24 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     };
 
     // ---------------- one-time setup
-    // One thread (lane 0 of the first issuer warp) initialises the barriers, starts the weight copy and issues the first image
-    // loads.  Nobody executes a generic->async proxy fence -- measured: that fence, executed by a thread that has TMA loads in
+    // The first issuer warp initialises the barriers (one lane each); its lane 0 then starts the weight copy and issues the
+    // first image loads.  Nobody executes a generic->async proxy fence -- measured: that fence, executed by a thread that has TMA loads in
     // flight, waits for them to land (~3 us per launch).
     if (kTrace && P.trace && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1024 + 2 * blockIdx.x] = (long long)gt; }
     const bool setup_thread = tid == n_wg * 128;
+    if (warp == n_wg * 4) {
+        // barrier init, one lane per barrier (29 mbarrier.init in a row by one thread took ~1100 cycles of every launch)
+        if (lane < 2 * kMaxStages) { if ((lane % kMaxStages) < n_st) mbar_init(&bar_full[lane / kMaxStages][lane % kMaxStages], 1); }
+        else if (lane < 2 * kMaxStages + kMaxWG * kMaxSlots) mbar_init(&bar_mma[0][0] + (lane - 2 * kMaxStages), 1);
+        else if (lane < 2 * kMaxStages + 2 * kMaxWG * kMaxSlots) mbar_init(&bar_ready[0][0] + (lane - 2 * kMaxStages - kMaxWG * kMaxSlots), kReadyArrivals);
+        else if (lane == 2 * kMaxStages + 2 * kMaxWG * kMaxSlots) mbar_init(&bar_w, 1);
+        fence_mbar_init();
+        __syncwarp();
+    }
     if (setup_thread) {
 #ifdef BNM_PREFETCH_TMAP
         tma_prefetch_desc(&tmap_in);   // the descriptor fetch (first TMA use) overlaps the barrier setup
 #endif
-        for (uint32_t s = 0; s < n_st; s++) { mbar_init(&bar_full[0][s], 1); mbar_init(&bar_full[1][s], 1); }
-        for (uint32_t g = 0; g < n_wg; g++)
-            for (int q = 0; q < kSlots; q++) { mbar_init(&bar_mma[g][q], 1); mbar_init(&bar_ready[g][q], kReadyArrivals); }
-        mbar_init(&bar_w, 1);
-        fence_mbar_init();
         if (kTrace && P.trace && blockIdx.x == 0) P.trace[1016] = clock64();   // barriers initialised
         // weight image -> smem with bulk async copies (same bytes for every CTA; L2-resident after the first wave).  The
         // async proxy writes them, so the tensor core may read them as soon as bar_w completes: no staging loop, no
