@@ -2,7 +2,7 @@
 // (/root/reference/BitNetMCU_MNIST_dll.c:95-121, kernels inference.c:88-208 + 23-72) as ONE persistent
 // sm_100a kernel.  Per 128-image tile:
 //
-//   TMA (cp.async.bulk.tensor, SWIZZLE_128B, evict-first)  images  HBM -> smem ring        [producer warp]
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B, evict-first)  images  HBM -> smem ring
 //   layer 1   tcgen05.mma kind::i8  A = smem image tile, B = decoded int8 weights (smem)  -> D int32 in TMEM
 //   ReLUNorm  tcgen05.ld (thread = image row): max -> shift -> clamp(x+r,0,cap)>>shift -> int8x4 pack
 //             -> tcgen05.st back into TMEM as the next layer's A operand (no smem / HBM round trip)
@@ -39,8 +39,7 @@ struct ChainParams {
     uint32_t stage_bytes;             // in_atoms * 128 rows * 128 B
     uint32_t n_stages, n_wg, n_slots;
     uint32_t w_bytes;                 // weight image bytes (multiple of 16)
-    uint32_t off_w, off_out;          // smem offsets (from the 1024-aligned base): weights, per-WG logits staging
-    uint32_t out_stage_bytes;         // per-WG staging bytes = 128 * n_classes * 4
+    uint32_t off_w;                   // smem offset (from the 1024-aligned base) of the weight image
     uint32_t tmem_wg_cols, tmem_a_off;
     uint32_t n_classes;
     uint32_t n_tiles;
@@ -124,15 +123,7 @@ __device__ __forceinline__ int max16(const uint32_t (&v)[16], int m) {
 // hidden-layer epilogue, the common 64-wide case: one TMEM load of the whole row, one TMEM store of the 16 packed words
 __device__ __forceinline__ void relunorm_tmem64(uint32_t d_addr, uint32_t a_addr) {
     uint32_t v[64];
-#ifdef BNM_LD_X16
-    {
-        uint32_t (&v4)[4][16] = reinterpret_cast<uint32_t (&)[4][16]>(v);
-#pragma unroll
-        for (int c = 0; c < 4; c++) tmem_ld_x16(d_addr + 16 * c, v4[c]);
-    }
-#else
     tmem_ld_x64(d_addr, v);
-#endif
     tmem_ld_wait();
     int mc[4];   // four independent max chains (ILP), merged at the end
 #pragma unroll
@@ -217,11 +208,7 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
 //           ready[g][slot] (128 arrivals: every epilogue thread has written A / finished reading D -> issuer may go on).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 2;
-#ifndef BNM_ARRIVE_ELECTED
 constexpr uint32_t kReadyArrivals = 128;   // every epilogue thread arrives
-#else
-constexpr uint32_t kReadyArrivals = 4;     // one elected lane per epilogue warp arrives
-#endif
 
 // layer-1 MMAs: A = image tile in smem (SWIZZLE_128B K-major), B = weight tiles.  Whole warp converged so that all
 // descriptor arithmetic stays in the uniform datapath; only the tcgen05 instructions are predicated on one lane.
@@ -310,9 +297,6 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         __syncwarp();
     }
     if (setup_thread) {
-#ifdef BNM_PREFETCH_TMAP
-        tma_prefetch_desc(&tmap_in);   // the descriptor fetch (first TMA use) overlaps the barrier setup
-#endif
         if (kTrace && P.trace && blockIdx.x == 0) P.trace[1016] = clock64();   // barriers initialised
         // weight image -> smem with bulk async copies (same bytes for every CTA; L2-resident after the first wave).  The
         // async proxy writes them, so the tensor core may read them as soon as bar_w completes: no staging loop, no
@@ -325,17 +309,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         // that one has completed and flushed (no-op without a programmatic dependency).  Every other access of this CTA
         // happens after a barrier that these loads complete, i.e. after this wait.
         if (P.wait_prior_grid) asm volatile("griddepcontrol.wait;" ::: "memory");
-#ifdef BNM_LOAD_ORDER
-        // first tile of every warpgroup before the second ones: the warpgroups start 1 tile-arrival apart instead of 2
-        for (uint32_t q = 0; q < (uint32_t)kSlots; q++)
-            for (uint32_t g = 0; g < n_wg; g++) {
-                const uint32_t i = g * kSlots + q;
-                if (i < n_st && i < my_tiles) issue_tile_load(i);
-            }
-        for (uint32_t i = n_virt; i < n_st && i < my_tiles; i++) issue_tile_load(i);
-#else
         for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
-#endif
         if (kTrace && P.trace && blockIdx.x == 0) P.trace[1017] = clock64();   // first loads issued
     } else if (warp == 1) {
         tmem_alloc<512>(&tmem_base_s);
@@ -362,11 +336,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 #pragma unroll 1
                 for (int q = 0; q < kSlots; q++) {
                     const uint32_t v = g * kSlots + q;
-#ifdef BNM_TILE_INTERLEAVE
-                    const uint32_t i = r * n_virt + q * n_wg + g;
-#else
                     const uint32_t i = r * n_virt + v;
-#endif
                     if (i >= my_tiles) continue;
                     const uint32_t d_tmem = tmem_base + v * P.tmem_wg_cols, a_tmem = d_tmem + P.tmem_a_off;
                     if (r != 0 || l != 0) {   // previous epilogue step of this slot: A written / D drained by all 4 warps
@@ -400,11 +370,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         uint32_t trace_n = 0;
 #define BNM_TRACE_POINT() do { if (kTrace && tracing && trace_n < 1000) P.trace[trace_n++] = clock64(); } while (0)
 
-        #ifdef BNM_TILE_INTERLEAVE
-        const uint32_t i_first = g, i_slot = n_wg;
-#else
         const uint32_t i_first = g * kSlots, i_slot = 1;
-#endif
         for (uint32_t r = 0, i0 = i_first; r < n_rounds; r++, i0 += n_virt)
             for (int l = 0; l < n_layers; l++) {
                 const uint32_t n_pad_l = P.n_pad[l];
@@ -562,16 +528,14 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
         if (const char *e = getenv("BNM_WG")) p.n_wg = std::max(1, std::min<int>((int)p.n_wg, atoi(e)));          // tuning knobs
         if (const char *e = getenv("BNM_SLOTS")) p.n_slots = std::max(1, std::min<int>((int)std::min<uint32_t>(kMaxSlots, fit / p.n_wg), atoi(e)));
     }
-    p.out_stage_bytes = round_up(kTileM * p.n_classes * 4, 128);
     const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*static*/;
-    p.off_w = 0;  // set below: stages first (1024-aligned), then weights, then staging
+    p.off_w = 0;  // set below: stages first (1024-aligned), then weights
     uint32_t fixed = round_up(p.w_bytes, 128);
     if (fixed + 2 * p.stage_bytes > smem_limit) { delete plan; return fail("fused path: weights do not fit in shared memory"); }
     p.n_stages = std::min<uint32_t>(kMaxStages, (smem_limit - fixed) / p.stage_bytes);
     p.n_stages = std::min<uint32_t>(p.n_stages, 6);
     p.off_w = p.n_stages * p.stage_bytes;
-    p.off_out = p.off_w + round_up(p.w_bytes, 128);
-    plan->smem_bytes = (size_t)p.off_out + 1024;
+    plan->smem_bytes = (size_t)p.off_w + round_up(p.w_bytes, 128) + 1024;
     for (int j = 0; j < 16; j++) p.kadd[j] = (uint32_t)j < p.n_classes ? 15 - j : -(1 << 30);
     plan->threads = p.n_wg * 160;   // 4 epilogue warps + 1 issuer warp per warpgroup
     plan->in_bytes = in_bytes;
