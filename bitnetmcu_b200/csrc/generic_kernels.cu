@@ -282,7 +282,7 @@ void launch_maxpool22(const int32_t *act, uint32_t xy, int32_t *out, size_t n, c
 // Fused CNN front-end for the 16x16 geometry (BitNetMCU_MNIST_dll.c:64-80).
 // thread = (image, channel).  conv1 (int8 x int8) runs on dp4a over 4-byte sliding windows that are built
 // once per image in shared memory and broadcast to all channel threads; conv2 (conv1 outputs are < 2^15: int8 x int8
-// x 9 >> 4 <= 9216) on dp2a over packed int16 pairs, 2 instructions per kernel row instead of 3 IMADs; conv3
+// x 9 >> 4 <= 9216) on dp2a over packed int16 pairs, 5 instructions per output instead of 9 IMADs; conv3
 // (int32 x int8) on IMAD; rolling line buffers in registers; pools folded in; ReLUNorm over the C*4 features of
 // an image via a shared-memory max.  n_shift is the literal 4 of dll.c:71-74.  Bound: the FMA pipe (IMAD/IDP issue).
 // ------------------------------------------------------------------------------------------------
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kCnnThreads) k_cnn_frontend16(const int8_t *__
     const bool active = t < ipb * C;
     const uint32_t il = active ? t / C : 0, ch = active ? t % C : 0;
 
-    int w1p[3], w2p[3], k3[9];   // per kernel row: (w0, w1, w2, 0) packed as int8x4
+    int w1p[3], w2p[3], k3[9], w2v, w2s;   // per kernel row: (w0, w1, w2, 0) packed as int8x4
     {
         const int8_t *a = w1 + ch * 9, *b = w2 + ch * 9, *c = w3 + ch * 9;
 #pragma unroll
@@ -310,6 +310,8 @@ __global__ void __launch_bounds__(kCnnThreads) k_cnn_frontend16(const int8_t *__
         }
 #pragma unroll
         for (int i = 0; i < 9; i++) k3[i] = c[i];
+        w2v = (int)((uint32_t)(uint8_t)b[2] | ((uint32_t)(uint8_t)b[5] << 8));   // third-column taps of rows 0 and 1
+        w2s = (int)(uint32_t)(uint8_t)b[8];                                      // third-column tap of row 2
     }
 
     const size_t n_groups = (n + ipb - 1) / ipb;
@@ -354,12 +356,13 @@ __global__ void __launch_bounds__(kCnnThreads) k_cnn_frontend16(const int8_t *__
                     int v[12];
 #pragma unroll
                     for (int x = 0; x < 12; x++) {
-                        int s = 0;
-#pragma unroll
-                        for (int dr = 0; dr < 3; dr++) {   // taps 0,1 from the pair at x, tap 2 from the pair at x+2
-                            s = __dp2a_lo((int)c1[(r + dr) % 3][x], w2p[dr], s);
-                            s = __dp2a_hi((int)c1[(r + dr) % 3][x + 2], w2p[dr], s);
-                        }
+                        // 9 taps in 5 dp2a: columns x, x+1 of the three rows as horizontal pairs; column x+2 of rows r, r+1 as a
+                        // vertical pair (one PRMT on the under-used ALU pipe); column x+2 of row r+2 alone
+                        int s = __dp2a_lo((int)c1[r % 3][x], w2p[0], 0);
+                        s = __dp2a_lo((int)c1[(r + 1) % 3][x], w2p[1], s);
+                        s = __dp2a_lo((int)c1[(r + 2) % 3][x], w2p[2], s);
+                        s = __dp2a_lo((int)__byte_perm(c1[r % 3][x + 2], c1[(r + 1) % 3][x + 2], 0x5410), w2v, s);
+                        s = __dp2a_lo((int)c1[(r + 2) % 3][x + 2], w2s, s);
                         v[x] = max(s, 0) >> 4;
                     }
                     if ((r & 1) == 0) {
