@@ -6,6 +6,8 @@
 //   * fused CNN front-end: conv,conv,pool,conv,pool per channel + ReLUNorm        (BitNetMCU_MNIST_dll.c:64-80)
 // These are the layer-by-layer path (BNM_PATH_LAYERS) and the front half of every CNN model; the fused
 // tcgen05 FC chain lives in fc_tcgen05.cu.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace bnm {
@@ -416,6 +418,10 @@ bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w
                          uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, cudaStream_t st) {
     if (xy != 16 || channels == 0 || channels > kCnnThreads) return false;
     if (n == 0) return true;
+    {   // conv1 on the tensor cores (cnn_tcgen05.cu): opt-in until validated on hardware
+        static const bool use_tc = [] { const char *e = getenv("BNM_CNN_TC"); return e && atoi(e) != 0; }();
+        if (use_tc && launch_cnn_frontend_tc(images, w1, w2, w3, channels, xy, features, feat_stride, n, sm_count, nullptr, st)) return true;
+    }
     uint32_t ipb = kCnnThreads / channels;
     size_t smem = (size_t)ipb * (64 + 224) * 4 + ipb * 4;
     size_t n_groups = (n + ipb - 1) / ipb;
