@@ -30,7 +30,12 @@ namespace bnm {
 constexpr int kTcThreads = 256;
 constexpr uint32_t kPlaneStride = 198;   // int16 per (image, channel) plane: 196 values + 2 pad = 99 words -> conflict-free over channels
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// kVer 1: 256 threads, all M tiles of a group in one MMA batch (up to 512 TMEM columns), one CTA per SM (validated, slow).
+// kVer 2: 128 threads, ipb = 128 / C images per group, one M tile at a time through a single 64-column accumulator, so three
+//         CTAs fit an SM (70 kB of shared memory, 64 TMEM columns each) and overlap each other's phases.  NOT yet run on
+//         hardware (written after the round's GPU budget was spent): BNM_CNN_TC=2.
+template <int kVer>
+__global__ void __launch_bounds__(kVer == 1 ? kTcThreads : 128, kVer == 1 ? 1 : 3)
 k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict__ w1, const int8_t *__restrict__ w2,
                     const int8_t *__restrict__ w3, uint32_t C, uint32_t n_pad, uint32_t ipb, uint32_t n_mtiles,
                     int8_t *__restrict__ feats, uint32_t feat_stride, size_t n, int *err) {
@@ -38,8 +43,9 @@ k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict_
     __shared__ __align__(8) uint64_t bar_mma;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_max[16];
-    const uint32_t t = threadIdx.x, lane = t & 31;
+    const uint32_t t = threadIdx.x, lane = t & 31, n_thr = blockDim.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+    constexpr uint32_t kTmemCols = kVer == 1 ? 512 : 64;
 
     uint8_t *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint32_t *s_img = reinterpret_cast<uint32_t *>(base);             // [ipb][64] words = 16 rows x 16 bytes
@@ -51,9 +57,9 @@ k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict_
 
     // ---- one-time setup
     if (t == 0) { mbar_init(&bar_mma, 1); fence_mbar_init(); }
-    if (warp == 1) tmem_alloc<512>(&tmem_base_s);
-    for (uint32_t i = t; i < n_mtiles * 256; i += kTcThreads) reinterpret_cast<uint4 *>(s_a)[i] = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = t; i < n_pad * 32; i += kTcThreads) {
+    if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_s);
+    for (uint32_t i = t; i < n_mtiles * 256; i += n_thr) reinterpret_cast<uint4 *>(s_a)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = t; i < n_pad * 32; i += n_thr) {
         const uint32_t nn = i >> 5, k = i & 31;
         const int8_t v = (nn < C && k < 9) ? w1[nn * 9 + k] : (int8_t)0;
         s_b[(nn >> 3) * 256 + (k >> 4) * 128 + (nn & 7) * 16 + (k & 15)] = (uint8_t)v;
@@ -84,13 +90,13 @@ k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict_
     for (size_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const size_t img_base = g * ipb;
         // ---- 1. images and their sliding windows
-        for (uint32_t idx = t; idx < ipb * 64; idx += kTcThreads) {
+        for (uint32_t idx = t; idx < ipb * 64; idx += n_thr) {
             const size_t img = img_base + idx / 64;
             s_img[idx] = img < n ? reinterpret_cast<const uint32_t *>(images)[img * 64 + (idx & 63)] : 0u;
         }
         if (t < ipb) s_max[t] = 0;
         __syncthreads();
-        for (uint32_t idx = t; idx < ipb * 224; idx += kTcThreads) {
+        for (uint32_t idx = t; idx < ipb * 224; idx += n_thr) {
             const uint32_t im = idx / 224, r = (idx % 224) / 14, x = idx % 14;
             const uint32_t lo = s_img[im * 64 + r * 4 + (x >> 2)];
             const uint32_t hi = (x >> 2) < 3 ? s_img[im * 64 + r * 4 + (x >> 2) + 1] : 0u;
@@ -98,7 +104,7 @@ k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict_
         }
         __syncthreads();
         // ---- 2. im2col rows: (a0 a1 a2 b0 | b1 b2 c0 c1 | c2 0 0 0 | 0 0 0 0) = taps in the order of w1[c][0..8]
-        for (uint32_t R = t; R < n_pos; R += kTcThreads) {
+        for (uint32_t R = t; R < n_pos; R += n_thr) {
             const uint32_t im = R / 196, pos = R % 196, y = pos / 14, x = pos % 14;
             const uint32_t *wrow = s_win + im * 224 + y * 14 + x;
             const uint32_t wa = wrow[0], wb = wrow[14], wc = wrow[28];
@@ -112,29 +118,16 @@ k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict_
         }
         fence_proxy_async_smem();   // the tensor core (async proxy) reads what these generic stores wrote
         __syncthreads();
-        // ---- 3. conv1 for all channels of all positions: one MMA per 128 positions
-        if (warp == 0) {
-            tc_fence_after();
-            if (elect_one()) {
-                for (uint32_t tile = 0; tile < n_mtiles; tile++)
-                    umma_i8_ss(tmem_base + tile * n_pad, make_smem_desc(smem_u32(s_a) + tile * 4096, 128, 256, UMMA_LAYOUT_NONE), b_desc, idesc, 0);
-                umma_commit(&bar_mma);
-            }
-            __syncwarp();
-        }
-        mbar_wait(&bar_mma, mma_phase, err, 7);
-        mma_phase ^= 1;
-        tc_fence_after();
-        // ---- 4. ReLU >> 4 -> int16 planes [image][channel][position]; thread = position row (TMEM lane), warps w and w+4 share
-        //         a lane quarter and take alternate tiles
-        for (uint32_t tile = warp >> 2; tile < n_mtiles; tile += 2) {
+        // ---- 3 + 4. conv1 for all channels of all positions (one MMA per 128 positions), then ReLU >> 4 -> int16 planes
+        //             [image][channel][position]; epilogue thread = position row (TMEM lane)
+        auto drain_tile = [&](uint32_t tile, uint32_t d_col) {
             const uint32_t R = tile * 128 + (warp & 3) * 32 + lane;
             const bool valid = R < n_pos;
             const uint32_t im = valid ? R / 196 : 0, pos = valid ? R % 196 : 0;
             uint16_t *dst = s_c1 + (size_t)im * C * kPlaneStride + pos;
             for (uint32_t c0 = 0; c0 < n_pad; c0 += 16) {
                 uint32_t x[16];
-                tmem_ld_x16(tmem_base + (((warp & 3) * 32) << 16) + tile * n_pad + c0, x);
+                tmem_ld_x16(tmem_base + (((warp & 3) * 32) << 16) + d_col + c0, x);
                 tmem_ld_wait();
                 if (valid) {
 #pragma unroll
@@ -142,9 +135,42 @@ k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict_
                         if (c0 + j < C) dst[(c0 + j) * kPlaneStride] = (uint16_t)(max((int)x[j], 0) >> 4);
                 }
             }
+        };
+        if (kVer == 1) {
+            if (warp == 0) {
+                tc_fence_after();
+                if (elect_one()) {
+                    for (uint32_t tile = 0; tile < n_mtiles; tile++)
+                        umma_i8_ss(tmem_base + tile * n_pad, make_smem_desc(smem_u32(s_a) + tile * 4096, 128, 256, UMMA_LAYOUT_NONE), b_desc, idesc, 0);
+                    umma_commit(&bar_mma);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&bar_mma, mma_phase, err, 7);
+            mma_phase ^= 1;
+            tc_fence_after();
+            // warps w and w+4 share a lane quarter and take alternate tiles
+            for (uint32_t tile = warp >> 2; tile < n_mtiles; tile += 2) drain_tile(tile, tile * n_pad);
+            tc_fence_before();
+            __syncthreads();
+        } else {
+            for (uint32_t tile = 0; tile < n_mtiles; tile++) {   // one accumulator, tile by tile; the other CTAs of the SM fill the gaps
+                if (warp == 0) {
+                    tc_fence_after();
+                    if (elect_one()) {
+                        umma_i8_ss(tmem_base, make_smem_desc(smem_u32(s_a) + tile * 4096, 128, 256, UMMA_LAYOUT_NONE), b_desc, idesc, 0);
+                        umma_commit(&bar_mma);
+                    }
+                    __syncwarp();
+                }
+                mbar_wait(&bar_mma, mma_phase, err, 7);
+                mma_phase ^= 1;
+                tc_fence_after();
+                drain_tile(tile, 0);
+                tc_fence_before();
+                __syncthreads();   // every warp has read D before the next MMA overwrites it
+            }
         }
-        tc_fence_before();
-        __syncthreads();
         // ---- 5. depthwise tail on the CUDA cores: thread = (image, channel)
         int f[4] = {0, 0, 0, 0};
         if (active) {
@@ -218,32 +244,39 @@ k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<512>(tmem_base);
+    if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // returns false when the shape is not covered (the caller then uses k_cnn_frontend16)
 bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
-                            uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err, cudaStream_t st) {
+                            uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err, int version,
+                            cudaStream_t st) {
     if (xy != 16 || channels < 16 || channels > 64) return false;
-    const uint32_t ipb = kTcThreads / channels;
+    const uint32_t threads = version == 2 ? 128 : kTcThreads;
+    const uint32_t ipb = threads / channels;
     if (ipb == 0 || ipb > 16) return false;
     const uint32_t n_pad = (channels + 15) / 16 * 16;
     const uint32_t n_mtiles = (ipb * 196 + 127) / 128;
-    if (n_mtiles * n_pad > 512) return false;
+    if (version != 2 && n_mtiles * n_pad > 512) return false;
     const size_t smem = 256 + (size_t)ipb * (64 + 224) * 4 + (size_t)n_mtiles * 4096 + (size_t)n_pad * 32 +
                         (size_t)ipb * channels * kPlaneStride * 2 + 64;
     if (smem > 226 * 1024) return false;
-    static size_t attr_bytes = 0;   // opt-in dynamic shared memory granted so far (static + dynamic must stay <= 227 kB)
-    if (smem > attr_bytes) {
-        if (cudaFuncSetAttribute(k_cnn_frontend16_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    static size_t attr_bytes[2] = {0, 0};   // opt-in dynamic shared memory granted so far (static + dynamic must stay <= 227 kB)
+    const int vi = version == 2 ? 1 : 0;
+    if (smem > attr_bytes[vi]) {
+        const cudaError_t e = vi ? cudaFuncSetAttribute(k_cnn_frontend16_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                 : cudaFuncSetAttribute(k_cnn_frontend16_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
             cudaGetLastError();   // not sticky: leave no stale error behind for the caller's launch check
             return false;
         }
-        attr_bytes = smem;
+        attr_bytes[vi] = smem;
     }
     const size_t n_groups = (n + ipb - 1) / ipb;
-    const unsigned grid = (unsigned)(n_groups < (size_t)sm_count ? n_groups : (size_t)sm_count);
-    k_cnn_frontend16_tc<<<grid, kTcThreads, smem, st>>>(images, w1, w2, w3, channels, n_pad, ipb, n_mtiles, features, feat_stride, n, d_err);
+    const size_t max_ctas = (size_t)sm_count * (vi ? 3 : 1);
+    const unsigned grid = (unsigned)(n_groups < max_ctas ? n_groups : max_ctas);
+    if (vi) k_cnn_frontend16_tc<2><<<grid, threads, smem, st>>>(images, w1, w2, w3, channels, n_pad, ipb, n_mtiles, features, feat_stride, n, d_err);
+    else k_cnn_frontend16_tc<1><<<grid, threads, smem, st>>>(images, w1, w2, w3, channels, n_pad, ipb, n_mtiles, features, feat_stride, n, d_err);
     return true;
 }
 

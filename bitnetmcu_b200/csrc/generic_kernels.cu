@@ -419,8 +419,8 @@ bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w
     if (xy != 16 || channels == 0 || channels > kCnnThreads) return false;
     if (n == 0) return true;
     {   // conv1 on the tensor cores (cnn_tcgen05.cu): opt-in until validated on hardware
-        static const bool use_tc = [] { const char *e = getenv("BNM_CNN_TC"); return e && atoi(e) != 0; }();
-        if (use_tc && launch_cnn_frontend_tc(images, w1, w2, w3, channels, xy, features, feat_stride, n, sm_count, nullptr, st)) return true;
+        static const int tc_version = [] { const char *e = getenv("BNM_CNN_TC"); return e ? atoi(e) : 0; }();
+        if (tc_version && launch_cnn_frontend_tc(images, w1, w2, w3, channels, xy, features, feat_stride, n, sm_count, nullptr, tc_version, st)) return true;
     }
     uint32_t ipb = kCnnThreads / channels;
     size_t smem = (size_t)ipb * (64 + 224) * 4 + ipb * 4;

@@ -42,7 +42,8 @@ bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w
 
 // same front-end with conv1 on tcgen05 (cnn_tcgen05.cu); false when the shape is not covered
 bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
-                            uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err, cudaStream_t st);
+                            uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err, int version,
+                            cudaStream_t st);
 
 // input quantisation ahead of the path (test_inference.py:140-141): float [n][elems] -> int8 [n][elems]
 void launch_quantize_images(const float *in, uint32_t elems, int8_t *out, size_t n, cudaStream_t st);
