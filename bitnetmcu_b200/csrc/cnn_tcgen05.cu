@@ -32,8 +32,8 @@ constexpr uint32_t kPlaneStride = 198;   // int16 per (image, channel) plane: 19
 
 // kVer 1: 256 threads, all M tiles of a group in one MMA batch (up to 512 TMEM columns), one CTA per SM (validated, slow).
 // kVer 2: 128 threads, ipb = 128 / C images per group, one M tile at a time through a single 64-column accumulator, so three
-//         CTAs fit an SM (70 kB of shared memory, 64 TMEM columns each) and overlap each other's phases.  NOT yet run on
-//         hardware (written after the round's GPU budget was spent): BNM_CNN_TC=2.
+//         CTAs fit an SM (70 kB of shared memory, 64 TMEM columns each) and overlap each other's phases.  BNM_CNN_TC=2:
+//         bit-exact on hardware for both CNN fixtures (tools/cnn_tc_debug.py); throughput not measured yet.
 template <int kVer>
 __global__ void __launch_bounds__(kVer == 1 ? kTcThreads : 128, kVer == 1 ? 1 : 3)
 k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict__ w1, const int8_t *__restrict__ w2,
