@@ -360,7 +360,8 @@ static int run_fc_layers(bnm_model *m, const int8_t *in, uint32_t in_stride, siz
     for (size_t l = 0; l < nl; l++) {
         const bool last = l + 1 == nl;
         int32_t *acc = last ? logits : m->d_acc;
-        launch_fc_dp4a(act, stride, m->fc[l], acc, n, st);
+        if (!launch_fc_dp4a(act, stride, m->fc[l], acc, n, st))
+            return fail(BNM_E_UNSUPPORTED, "FC layer %zu: %u inputs need more shared memory than an SM has (layer kernel stages 128 rows)", l, m->fc[l].n_in);
         if (last) {
             if (labels) launch_relunorm(acc, m->fc[l].n_out, nullptr, 0, labels, n, st);
         } else {
@@ -523,9 +524,28 @@ extern "C" int bnm_processfclayer_batch(const int8_t *activations, const uint32_
     CU_TRY(cudaMemcpy(&f, flag.p, 4, cudaMemcpyDeviceToHost));
     if (f) { L.dense_b = db.as<int8_t>(); L.quad_b = qb.as<int4>(); }
     CU_TRY(cudaMemset(act.p, 0, n * (size_t)L.k_pad));
-    // ternary layers declare a padded n_input (exportquant.py:166) while the caller's rows hold n_input bytes
-    CU_TRY(cudaMemcpy2D(act.p, L.k_pad, activations, n_input, n_input, n, cudaMemcpyHostToDevice));
-    launch_fc_dp4a(act.as<int8_t>(), L.k_pad, L, out.as<int32_t>(), n, 0);
+    // Ternary layers declare n_input padded to a multiple of 10 with zero trits (exportquant.py:132-137,166) and the
+    // reference never reads the activations under a zero trit (inference.c:128): a caller may hand in a 256-byte row for
+    // n_input = 260.  Read exactly what the reference can read: up to the last non-zero trit of any row.
+    uint32_t valid_in = n_input;
+    if (enc == BNM_ENC_TERNARY) {
+        const uint16_t *w16 = reinterpret_cast<const uint16_t *>(weights);
+        const uint32_t wpr = n_input / 10;
+        valid_in = 0;
+        for (uint32_t o = 0; o < n_output; o++)
+            for (uint32_t g = wpr; g-- > 0;) {
+                if (g * 10 + 10 <= valid_in) break;
+                uint32_t c = w16[(size_t)o * wpr + g];
+                for (uint32_t j = 0; j < 10; j++) {
+                    c *= 3u;
+                    if (!(c & 0x20000u)) valid_in = std::max(valid_in, g * 10 + j + 1);
+                    c &= 0xFFFFu;
+                }
+            }
+    }
+    if (valid_in) CU_TRY(cudaMemcpy2D(act.p, L.k_pad, activations, n_input, valid_in, n, cudaMemcpyHostToDevice));
+    if (!launch_fc_dp4a(act.as<int8_t>(), L.k_pad, L, out.as<int32_t>(), n, 0))
+        return fail(BNM_E_UNSUPPORTED, "processfclayer: n_input %u needs more shared memory than an SM has (layer kernel stages 128 rows)", n_input);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpy(output, out.p, n * (size_t)n_output * 4, cudaMemcpyDeviceToHost));
     return 0;

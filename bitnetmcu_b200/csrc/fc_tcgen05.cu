@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "kernels.h"
@@ -65,6 +66,17 @@ struct FcChainPlan {
     int sm_count = 0;
     int device = 0;
     int overlap = 0;                  // BNM_OPT_LAUNCH_OVERLAP: 0 plain launch, 1 dependent launch + wait, 2 independent launches
+    // launch-path state (nothing on the launch path reads the environment or re-encodes a known tensor map)
+    struct TmapSlot { const void *ptr = nullptr; size_t n = 0; CUtensorMap map; };
+    TmapSlot tmaps[4];                // tensor maps of the most recent (pointer, n) pairs: double/triple-buffered callers hit every time
+    unsigned tmap_next = 0;
+    std::string trace_path;           // BNM_TRACE (diagnostics build path), read once at plan creation
+    int stagger_override = -1;        // BNM_STAGGER_NS in cycles, read once at plan creation (-1: not set)
+    // mode 2 bookkeeping: the buffers of the previous launch on this plan (the promise "consecutive launches are independent" is
+    // checked as far as the library can see it: a launch that reuses a buffer of the one before keeps the grid-dependency wait)
+    const void *prev_in = nullptr, *prev_logits = nullptr, *prev_labels = nullptr;
+    cudaStream_t prev_stream = nullptr;
+    bool prev_valid = false;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -247,7 +259,8 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
     if (kTrace && P.trace && blockIdx.x == 0 && tid == 0) P.trace[1020] = clock64();   // kernel entry
     // Programmatic dependent launch: the next kernel in the stream may take over each SM as soon as this CTA leaves it (it
-    // cannot co-reside: shared memory and TMEM are fully used), so its launch latency and prologue -- and, when the caller
+    // cannot co-reside: every launch asks for more than half of the SM's shared memory, fc_chain_plan_create), so its launch
+    // latency and prologue -- and, when the caller
     // declares consecutive launches independent, its first tiles -- overlap the ragged end of this one.
     // Only when the grid fills the GPU (one CTA per SM): then launch k+1 can start no CTA before the matching CTA of launch k
     // has left, and launch k+2 none before all of launch k are gone -- at most two consecutive launches ever overlap.  A
@@ -536,6 +549,12 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     p.n_stages = std::min<uint32_t>(p.n_stages, 6);
     p.off_w = p.n_stages * p.stage_bytes;
     plan->smem_bytes = (size_t)p.off_w + round_up(p.w_bytes, 128) + 1024;
+    // One CTA per SM is part of the launch-overlap contract (launch k+2 must never run next to launch k on an SM): registers and
+    // TMEM do not enforce it (launch_dependents fires before tmem_alloc blocks), shared memory does once a CTA asks for more than
+    // half of the SM's 227 kB.
+    plan->smem_bytes = std::max<size_t>(plan->smem_bytes, 116 * 1024);
+    if (const char *e = getenv("BNM_TRACE")) plan->trace_path = e;                                   // diagnostics, read once
+    if (const char *e = getenv("BNM_STAGGER_NS")) plan->stagger_override = (int)(atof(e) * 1.8);     // tuning knob; ~1.8 cycles per ns under load
     for (int j = 0; j < 16; j++) p.kadd[j] = (uint32_t)j < p.n_classes ? 15 - j : -(1 << 30);
     plan->threads = p.n_wg * 160;   // 4 epilogue warps + 1 issuer warp per warpgroup
     plan->in_bytes = in_bytes;
@@ -573,6 +592,7 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
 void fc_chain_plan_set_overlap(FcChainPlan *p, int mode) {
     if (!p) return;
     p->overlap = mode;
+    p->prev_valid = false;
     // Overlapped launches find HBM uncongested, all six first tiles of a CTA land within ~1 us and the three warpgroups
     // would run in lockstep, competing for the ALU pipe at the same moments (measured -3 %).  Start warpgroup g no earlier
     // than g x 2 us after kernel entry (a third of the ~6 us round).  Plain launches get the same offsets for free from
@@ -587,6 +607,24 @@ void fc_chain_plan_destroy(FcChainPlan *p) {
     delete p;
 }
 
+static const CUtensorMap *plan_tensor_map(FcChainPlan *plan, const int8_t *in, size_t n) {
+    for (auto &t : plan->tmaps)
+        if (t.ptr == in && t.n == n) return &t.map;
+    FcChainPlan::TmapSlot &t = plan->tmaps[plan->tmap_next++ % 4];
+    memset(&t.map, 0, sizeof(t.map));
+    cuuint64_t gdim[2] = {(cuuint64_t)plan->in_bytes, (cuuint64_t)n};
+    cuuint64_t gstride[1] = {(cuuint64_t)plan->in_bytes};
+    cuuint32_t box[2] = {128, (cuuint32_t)kTileM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(&t.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(in), gdim, gstride, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { t.ptr = nullptr; t.n = 0; return nullptr; }
+    t.ptr = in;
+    t.n = n;
+    return &t.map;
+}
+
 int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st) {
     if (n == 0) return 0;
     if (n > 0x7fffff00ull) return -2;
@@ -595,24 +633,23 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     p.labels = labels;
     p.n = n;
     p.n_tiles = (uint32_t)((n + kTileM - 1) / kTileM);
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    cuuint64_t gdim[2] = {(cuuint64_t)plan->in_bytes, (cuuint64_t)n};
-    cuuint64_t gstride[1] = {(cuuint64_t)plan->in_bytes};
-    cuuint32_t box[2] = {128, (cuuint32_t)kTileM};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = get_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(in), gdim, gstride, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return -3;
+    const CUtensorMap *tmap_p = plan_tensor_map(plan, in, n);
+    if (!tmap_p) return -3;
+    const CUtensorMap &tmap = *tmap_p;
     unsigned grid = (unsigned)std::min<uint32_t>(p.n_tiles, (uint32_t)plan->sm_count);
     long long *d_trace = nullptr;
-    const char *trace_path = getenv("BNM_TRACE");
+    const char *trace_path = plan->trace_path.empty() ? nullptr : plan->trace_path.c_str();
     if (trace_path) { cudaMalloc(&d_trace, 2048 * sizeof(long long)); cudaMemset(d_trace, 0, 2048 * sizeof(long long)); }
     p.trace = d_trace;
-    p.wait_prior_grid = plan->overlap != 2;
+    // Mode 2 drops the grid-dependency wait, i.e. EVERY ordering against the work enqueued before this launch on the stream
+    // (the previous bnm launch and any producer kernel of `images` alike).  The library keeps the wait whenever it can see the
+    // promise being broken: first launch on this plan / another stream / a buffer of the previous launch reused.
+    bool independent = plan->overlap == 2 && plan->prev_valid && plan->prev_stream == st && in != plan->prev_in &&
+                       logits != plan->prev_logits && (labels == nullptr || labels != plan->prev_labels);
+    p.wait_prior_grid = !independent;
     p.early_trigger = plan->overlap != 0 && grid == (unsigned)plan->sm_count;
-    if (const char *e = getenv("BNM_STAGGER_NS")) p.stagger_cycles = (uint32_t)(atof(e) * 1.8);   // tuning knob; ~1.8 cycles per ns under load
+    if (plan->stagger_override >= 0) p.stagger_cycles = (uint32_t)plan->stagger_override;
+    plan->prev_in = in; plan->prev_logits = logits; plan->prev_labels = labels; plan->prev_stream = st; plan->prev_valid = true;
     if (trace_path) {
         if (p.n_slots == 1) fc_chain_kernel<1, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
         else fc_chain_kernel<2, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);

@@ -145,19 +145,24 @@ __global__ void __launch_bounds__(128) k_fc_dp4a(const int8_t *__restrict__ act,
     }
 }
 
-void launch_fc_dp4a(const int8_t *act, uint32_t act_stride, const FcLayerDev &L, int32_t *out, size_t n, cudaStream_t st) {
-    if (n == 0) return;
+bool launch_fc_dp4a(const int8_t *act, uint32_t act_stride, const FcLayerDev &L, int32_t *out, size_t n, cudaStream_t st) {
+    if (n == 0) return true;
     uint32_t k4n = L.k_pad / 4;
     size_t smem = (size_t)128 * (k4n + 1) * 4;
+    if (smem > 227 * 1024) return false;   // 128 staged rows of more than ~1.8k inputs do not fit an SM
     unsigned grid = (unsigned)((n + 127) / 128);
     uint32_t valid = act_stride < L.k_pad ? act_stride : L.k_pad;
-    if (L.dense_b) {
-        cudaFuncSetAttribute(k_fc_dp4a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_fc_dp4a<true><<<grid, 128, smem, st>>>(act, act_stride, valid, L.quad_a, L.quad_b, k4n, L.n_out, L.n_pad, out, n);
-    } else {
-        cudaFuncSetAttribute(k_fc_dp4a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_fc_dp4a<false><<<grid, 128, smem, st>>>(act, act_stride, valid, L.quad_a, L.quad_a, k4n, L.n_out, L.n_pad, out, n);
+    static size_t granted[2] = {48 * 1024, 48 * 1024};   // opt-in dynamic shared memory granted so far, per instantiation
+    const int vi = L.dense_b ? 1 : 0;
+    if (smem > granted[vi]) {
+        const cudaError_t e = vi ? cudaFuncSetAttribute(k_fc_dp4a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                 : cudaFuncSetAttribute(k_fc_dp4a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { cudaGetLastError(); return false; }
+        granted[vi] = smem;
     }
+    if (vi) k_fc_dp4a<true><<<grid, 128, smem, st>>>(act, act_stride, valid, L.quad_a, L.quad_b, k4n, L.n_out, L.n_pad, out, n);
+    else k_fc_dp4a<false><<<grid, 128, smem, st>>>(act, act_stride, valid, L.quad_a, L.quad_a, k4n, L.n_out, L.n_pad, out, n);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------

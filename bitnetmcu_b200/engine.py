@@ -85,7 +85,11 @@ class Engine:
     # ---- device pointers (torch tensors as plumbing) ---------------------------------------------------
     def infer_device(self, images, logits, labels=None, stream: Optional[int] = None) -> None:
         """images: torch.int8 [n, img_bytes] on this GPU; logits: torch.int32 [n, n_classes]; labels: torch.int32/uint32 [n]
-        or None.  Asynchronous on ``stream`` (a cudaStream_t as int; default: torch's current stream)."""
+        or None.  Asynchronous on ``stream`` (a cudaStream_t as int; default: torch's current stream).
+
+        With ``OPT_LAUNCH_OVERLAP`` = 2 a launch whose buffers differ from the previous call's is NOT ordered against earlier
+        work on the stream (include/bitnetmcu_b200.h): its images must already be complete when the previous call was
+        enqueued.  Chains such as ``quantize_images_device`` -> ``infer_device`` on one stream need mode 0 or 1."""
         import torch
         n = images.shape[0]
         if stream is None:

@@ -167,6 +167,16 @@ class Model:
         return _BLOB_HDR.pack(BLOB_MAGIC, self.model_class, len(self.layers), self.img_bytes) + b"".join(entries) + bytes(data)
 
     @staticmethod
+    def reference_layer_names(model_class: int, kinds: List[int]) -> List[str]:
+        """The ``L<k>`` names the reference's harnesses compile against (the blob does not store names): FC models
+        ``L1..Ln`` (BitNetMCU_MNIST_dll.c:95-121, BitNetMCU_model_fc.h), CNN models the module-enumeration indices of the
+        shipped header -- conv L2, conv L4, pool L6, conv L7, pool L9, then FC L11, L13, L15, ...
+        (BitNetMCU_MNIST_dll.c:64-90, BitNetMCU_model_cnn.h)."""
+        if model_class == MODEL_CNNMNIST and kinds[:5] == [LAYER_CONV33, LAYER_CONV33, LAYER_MAXPOOL22, LAYER_CONV33, LAYER_MAXPOOL22]:
+            return ["L2", "L4", "L6", "L7", "L9"] + [f"L{11 + 2 * i}" for i in range(len(kinds) - 5)]
+        return [f"L{i + 1}" for i in range(len(kinds))]
+
+    @staticmethod
     def from_blob(blob: bytes, source: str = "") -> "Model":
         magic, cls, n_layers, img_bytes = _BLOB_HDR.unpack_from(blob, 0)
         if magic != BLOB_MAGIC:
@@ -181,6 +191,8 @@ class Model:
                 w = np.frombuffer(blob, dtype=dt, count=nbytes // np.dtype(dt).itemsize, offset=off).copy()
             m.layers.append(Layer(kind=kind, name=f"L{i}", bitperweight=bpw, n_in=n_in, n_out=n_out,
                                   in_channels=in_ch, groups=groups, weights=w))
+        for l, name in zip(m.layers, Model.reference_layer_names(cls, [l.kind for l in m.layers])):
+            l.name = name
         m.validate()
         return m
 

@@ -93,8 +93,16 @@ enum { BNM_OPT_PATH = 1, BNM_OPT_NF4_EXTENSION = 2, BNM_OPT_CHUNK_IMAGES = 3, BN
  *   2  the caller declares consecutive launches independent -- the images / logits / labels of one call are not the
  *      buffers of the call right before it (e.g. double-buffered batches), exactly what issuing them on two streams would
  *      promise.  The next launch's tiles then start on each SM as the previous launch leaves it (-6 ... -9 % per step).
- *      Only launches that fill the GPU (>= one 128-image tile per SM) trigger early: at most two consecutive launches are
- *      ever in flight together.  CNN models are held at mode 1 (the front-end kernel really feeds the FC kernel). */
+ *      CONTRACT: an independent launch executes no grid-dependency wait, so it is ordered against NOTHING enqueued before it
+ *      on the stream -- neither the previous bnm launch nor a producer kernel / copy that writes `images`.  The images of
+ *      call k must therefore be complete before call k-1 was enqueued (resident inputs, or produced on another stream and
+ *      joined by an event before call k-1).  The library keeps ordinary stream semantics (the wait) for every launch where it
+ *      can see the promise broken: the first launch after the option is set, a launch on another stream than the one before,
+ *      and a launch that reuses the images, logits or labels pointer of the one before.  Producer -> inference chains on one
+ *      stream (bnm_quantize_images_device then bnm_infer_batch_device) belong to mode 0 or 1.
+ *      Only launches that fill the GPU (>= one 128-image tile per SM) trigger early, and every launch occupies its SM
+ *      exclusively (more than half of the shared memory): at most two consecutive launches are ever in flight together.
+ *      CNN models are held at mode 1 (the front-end kernel really feeds the FC kernel). */
 BNM_API int bnm_version(void);
 BNM_API const char *bnm_last_error(void);           /* thread-local text of the last failure */
 BNM_API int bnm_device_count(void);                 /* 0 when no CUDA device is usable        */

@@ -406,3 +406,94 @@ def test_float_images_to_labels_on_device(lib, oracle):
     assert np.array_equal(d_q.cpu().numpy(), q)
     assert np.array_equal(d_log.cpu().numpy(), want_logits) and np.array_equal(d_lab.cpu().numpy().astype(np.uint32), want_labels)
     e.close()
+
+
+# ---- function-level parity on the tensor-core path --------------------------------------------
+# processfclayer (inference.c:88-208) through fc_chain_kernel itself: a one-layer model's logits ARE the layer's output.
+
+_FUSED_SINGLE = [(256, 64), (64, 10), (160, 160), (320, 7), (32, 1), (256, 17), (256, 37), (128, 250), (768, 10)]
+
+
+@pytest.mark.parametrize("enc", [1, 2, 4, 12, 16, 20, 64])
+def test_processfclayer_on_tcgen05(lib, oracle, enc):
+    """Single-layer models over the (n_in, n_out) grid incl. 320->7, 160->160, ternary-padded widths and n_out in {17, 37,
+    250} (> 16 classes: the chunked logits/argmax epilogue), both kernels, against the oracle's processfclayer + ReLUNorm."""
+    from bitnetmcu_b200 import _lib, model as M, pack as P
+    from bitnetmcu_b200.engine import Engine
+    rng = np.random.default_rng(100 + enc)
+    for n_in, n_out in _FUSED_SINGLE:
+        if enc == 1 and n_in % 32:
+            continue
+        m = P.random_fc_model(enc, (n_in, n_out), seed=enc * 1000 + n_in + n_out)
+        m.img_bytes = n_in                      # ternary: the layer declares the padded width, the image keeps n_in bytes
+        imgs = rng.integers(-128, 128, size=(777, n_in)).astype(np.int8)
+        imgs[:16] = -128
+        imgs[16:32] = 127
+        want, want_lab = oracle.infer(m, imgs)
+        L = m.layers[0]
+        row = oracle.fclayer(np.pad(imgs[40], (0, L.n_in - n_in)), L.weights, enc, L.n_in, n_out)
+        assert np.array_equal(want[40], row)
+        for path in (_lib.PATH_TCGEN05, _lib.PATH_LAYERS):
+            e = Engine(m, path=path)
+            assert e.active_path == path
+            lo, la = e.infer(imgs)
+            assert np.array_equal(lo, want), (enc, n_in, n_out, path, np.argwhere(lo != want)[:4])
+            assert np.array_equal(la, want_lab), (enc, n_in, n_out, path)
+            e.close()
+
+
+@pytest.mark.parametrize("enc", [2, 4, 12, 16, 20, 64, 1])
+@pytest.mark.parametrize("widths", [(256, 96, 64, 37), (256, 160, 160, 17), (256, 48, 250), (256, 16, 16, 10), (64, 224, 32, 20),
+                                    (256, 64, 64, 64, 64, 64, 64, 64, 10)])
+def test_chains_on_tcgen05(lib, oracle, enc, widths):
+    """Random-code chains with odd shapes: A-from-TMEM (.ts) layers of every width class (16..224), the wide two-pass
+    ReLUNorm, FP130 with +128 (residual plane) in EVERY layer, > 16 classes, the 8-layer maximum."""
+    from bitnetmcu_b200 import _lib, pack as P
+    from bitnetmcu_b200.engine import Engine
+    if enc == 1 and any(w % 32 for w in widths[:-1]):
+        widths = tuple((w + 31) // 32 * 32 for w in widths[:-1]) + (widths[-1],)
+    if enc == 2 and any(w % 16 for w in widths[:-1]):
+        pytest.skip("2bitsym rows need n_in % 16 == 0")
+    m = P.random_fc_model(enc, widths, seed=enc + sum(widths))
+    m.img_bytes = widths[0]
+    rng = np.random.default_rng(sum(widths))
+    imgs = rng.integers(-128, 128, size=(1500 + 11, widths[0])).astype(np.int8)
+    imgs[:50] = np.clip(imgs[:50], 0, 127)
+    want, want_lab = oracle.infer(m, imgs)
+    e = Engine(m, path=_lib.PATH_TCGEN05)
+    lo, la = e.infer(imgs)
+    assert np.array_equal(lo, want), (enc, widths, np.argwhere(lo != want)[:4])
+    assert np.array_equal(la, want_lab)
+    e.close()
+
+
+def test_launch_overlap_mode2_reused_buffers_keep_stream_order(lib, oracle):
+    """mode 2 drops the grid-dependency wait only for launches whose buffers differ from the previous call's.
+    Reusing the SAME buffers with a producer copy in front of every launch (the pattern mode 2 does not promise) must still
+    be ordered: the library falls back to the wait when it sees a pointer of the previous launch again."""
+    import torch
+    from bitnetmcu_b200 import _lib
+    m = load_model("fc")
+    n = 148 * 128 * 5 + 3
+    batches = [_rand_images(n, seed=40 + k) for k in range(4)]
+    want = [oracle.infer(m, b) for b in batches]
+    e = _engine("fc", 0)
+    e.set_option(_lib.OPT_LAUNCH_OVERLAP, 2)
+    s = torch.cuda.Stream()
+    src = [torch.from_numpy(b).cuda() for b in batches]
+    d_img = torch.empty_like(src[0])
+    d_log = torch.empty((n, 10), dtype=torch.int32, device="cuda")
+    d_lab = torch.empty(n, dtype=torch.int32, device="cuda")
+    got = []
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        for rep in range(3):
+            for k in range(4):
+                d_img.copy_(src[k])
+                e.infer_device(d_img, d_log, d_lab)
+                if rep == 2:
+                    got.append((d_log.clone(), d_lab.clone()))
+        s.synchronize()
+    for (gl, gb), (wl, wb) in zip(got, want):
+        assert np.array_equal(gl.cpu().numpy(), wl) and np.array_equal(gb.cpu().numpy().astype(np.uint32), wb)
+    e.close()

@@ -21,10 +21,9 @@ def _build(tmp, name):
     from bitnetmcu_b200 import _lib
     from bitnetmcu_b200.pack import write_header
     m = load_model(name)
-    # the reference's dll.c names FC layers L1..L4 / CNN layers L2..L15 (dll.c:48-121)
-    names = ["L2", "L4", "L6", "L7", "L9", "L11", "L13", "L15"] if m.model_class == 1 else ["L1", "L2", "L3", "L4"]
-    for l, n in zip(m.layers, names):
-        l.name = n
+    # Model.load names the layers as the reference's dll.c expects: FC L1..L4 / CNN L2..L15 (dll.c:48-121)
+    want = ["L2", "L4", "L6", "L7", "L9", "L11", "L13", "L15"] if m.model_class == 1 else ["L1", "L2", "L3", "L4"]
+    assert [l.name for l in m.layers] == want[:len(m.layers)]
     write_header(m, os.path.join(tmp, "BitNetMCU_model.h"))
     d = np.load(os.path.join(GOLDEN, "digits.npz"))
     _write_test_data_header(os.path.join(tmp, "BitNetMCU_MNIST_test_data.h"), d["images"], d["labels"])
