@@ -8,25 +8,37 @@ A "step" = one pass of the whole chain (processfclayer x4 + ReLUNorm x4, BitMnis
 batch of synthetic int8 images resident in HBM.  N > 1: launched by torchrun, one rank per GPU, the batch shards by
 rank with no data-path collective (weak scaling: 1M images per GPU).  Prints ONE JSON line on rank 0.
 
-value      : whole-job images/s, device-timed (CUDA events), max over ranks, inputs resident in HBM
-e2e        : same metric through bnm_infer_batch with PINNED HOST buffers, H2D + D2H inside the timed region
-roofline   : dominant kernel fc_chain_kernel: 296 algorithmic B/image x batch / mean launch duration (CUDA events)
-cpu_baseline: the reference's own C code (oracle/_ref, all host cores) on a bounded sample, rank 0, N = 1
+value        : whole-job images/s, device-timed (CUDA events), max over ranks, inputs resident in HBM, PLAIN launches
+               (ordinary stream semantics: what a drop-in caller gets by default)
+value_overlapped_launches : same steps with BNM_OPT_LAUNCH_OVERLAP = 2 (consecutive launches declared independent; the
+               bench double-buffers inputs and outputs, which is what that mode asks for)
+value_sustained: >= 1 s of back-to-back plain launches, with the nvidia-smi clock sampler covering THAT region
+e2e          : same metric through bnm_infer_batch with PINNED HOST buffers, H2D + D2H inside the timed region
+roofline     : dominant kernel fc_chain_kernel: 296 algorithmic B/image x batch / mean launch duration (CUDA events)
+configs      : every other BASELINE.json config (Binary-160, Ternary-64, 2bitsym-96, CNN-64, CNN-48 at 2^20; FC at 2^22),
+               each with value, roofline against its real bound (HBM, or the integer-ALU pipe for the CNN front-end) and a
+               full-batch parity flag against the oracle
+latency_us_batch1: the drop-in Inference() (gcc-built shim, one image per call) next to the reference DLL's Inference()
+cpu_baseline : the reference's own C code (oracle/_ref, all host cores) on a bounded sample, rank 0, N = 1
 --impl reference: that CPU reference as the timed arm (rank 0 only)
 """
 import argparse
+import ctypes as Ct
 import json
 import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
+import zlib
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
 
 def _baseline_metric():
     """The headline metric, verbatim from BASELINE.json (the achieved-HBM half of it is the `roofline` object)."""
@@ -40,18 +52,23 @@ def _baseline_metric():
 METRIC = _baseline_metric()
 UNIT = "images/s"
 
+# BASELINE.json configs 3-5 besides the headline (config 2): (fixture model, images per GPU)
+EXTRA_CONFIGS = [("binary160", 1 << 20), ("ternary64", 1 << 20), ("2bitsym96", 1 << 20), ("cnn", 1 << 20), ("cnn_48", 1 << 20),
+                 ("fc", 1 << 22)]
+
 
 def load_model(name):
     from bitnetmcu_b200.model import Model
     return Model.load(os.path.join(ROOT, "tests", "golden", "models", name + ".bnm"))
 
 
-def measured_peak_gbs():
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
 
 
 def synth_images(n, img_bytes, seed, dist="uniform"):
@@ -80,18 +97,33 @@ def synth_images(n, img_bytes, seed, dist="uniform"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING a timed region (B200_PROFILING.md recipe).  Auxiliary: whatever
+    goes wrong here (UUID-style CUDA_VISIBLE_DEVICES, no nvidia-smi) must never abort the measurement."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
+    @staticmethod
+    def device_selector(local_rank):
+        """What to hand to `nvidia-smi -i`: an index or a UUID string, from CUDA_VISIBLE_DEVICES when it is set."""
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").strip()
+        try:
+            if vis:
+                items = [v.strip() for v in vis.split(",") if v.strip()]
+                item = items[local_rank] if local_rank < len(items) else items[0]
+                return item            # "3" or "GPU-xxxx" / "MIG-...": nvidia-smi -i takes either
+            import torch
+            return str(torch.cuda.current_device())
+        except Exception:
+            return str(local_rank)
+
+    def __init__(self, selector):
+        self.sel = str(selector)
         self.lines = []
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -99,26 +131,34 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+        try:
+            for line in self.proc.stdout:
+                self.lines.append((time.perf_counter(), line.strip()))
+        except Exception:
+            pass
 
-    def stop(self, t0, t1):
+    def stop(self, t0, t1, region):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "region": region}
         time.sleep(0.15)
-        self.proc.terminate()
-        rows = [l.split(", ") for t, l in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l.split(", ") for _, l in self.lines]
-        sm, smax, reasons = [], [], set()
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+        inside = [l.split(", ") for t, l in self.lines if t0 <= t <= t1]
+        rows = inside or [l.split(", ") for t, l in self.lines if t0 - 0.1 <= t <= t1 + 0.2] or [l.split(", ") for _, l in self.lines]
+        sm, smax, power, reasons = [], [], [], set()
         for r in rows:
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.strip().lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_inside_region": len(inside), "region": region}
 
 
 def host_cpu_budget():
@@ -133,6 +173,11 @@ def host_cpu_budget():
     except Exception:
         pass
     return n, quota
+
+
+def checker_threads():
+    ncpu, quota = host_cpu_budget()
+    return max(1, int(quota + 0.5)) if quota else ncpu
 
 
 def cpu_reference_rate(model, images, budget_s=1.0, reps=3):
@@ -189,15 +234,15 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int8", "data": "synthetic" if args.dist == "uniform" else "synthetic (MNIST-like value profile)",
-        "config": {"workload": workload_name(args, model), "batch_per_gpu": args.batch, "sample_per_step": n},
+        "config": {"workload": workload_name(args.model, model, args.batch), "batch_per_gpu": args.batch, "sample_per_step": n},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), file=RESULT_OUT, flush=True)
 
 
-def workload_name(args, model):
-    return f"{args.model}: {model.describe()} | batch {args.batch} x {model.img_bytes} B int8 per GPU"
+def workload_name(name, model, batch):
+    return f"{name}: {model.describe()} | batch {batch} x {model.img_bytes} B int8 per GPU"
 
 
 RESULT_OUT = sys.stdout
@@ -213,6 +258,190 @@ def claim_stdout():
     os.dup2(2, 1)
 
 
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# measurement helpers (GPU arm)
+# ------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """torch plumbing shared by the measurements of one process / rank."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as tdist
+        from bitnetmcu_b200 import dist as bdist
+        self.torch, self.tdist = torch, tdist
+        self.rank, self.local_rank, self.world = bdist.env_rank_world()
+        if self.world > 1:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's INFO log: stderr, not stdout (see claim_stdout)
+            bdist.init_process_group("nccl")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.stream = torch.cuda.current_stream(self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.tdist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.tdist.all_reduce(t, op=self.tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_steps(self, step, steps, warmup):
+        """warmup untimed steps, then exactly `steps` steps between two events on the launching stream, barrier + synchronize on
+        both sides; returns (max-over-ranks ms per step, this rank's ms per step)."""
+        torch = self.torch
+        for i in range(warmup):
+            step(i)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for i in range(steps):
+            step(i)
+        e1.record(self.stream)
+        self.barrier()
+        local = e0.elapsed_time(e1) / steps
+        return self.max_over_ranks(local), local
+
+
+class DeviceBatch:
+    """Two image buffers alternated per step (each n x 256 B = 268 MB at 1M: larger than the 126 MB L2) and double-buffered
+    outputs: consecutive launches touch disjoint buffers."""
+
+    def __init__(self, ctx, eng, host_imgs):
+        torch = ctx.torch
+        n, C = host_imgs.shape[0], eng.n_classes
+        self.n = n
+        self.d_in = [torch.from_numpy(host_imgs).to(ctx.dev), torch.from_numpy(np.ascontiguousarray(host_imgs[::-1])).to(ctx.dev)]
+        self.d_logits = [torch.empty((n, C), dtype=torch.int32, device=ctx.dev) for _ in range(2)]
+        self.d_labels = [torch.empty(n, dtype=torch.int32, device=ctx.dev) for _ in range(2)]
+        self.eng, self.ctx = eng, ctx
+
+    def step(self, i):
+        self.eng.infer_device(self.d_in[i & 1], self.d_logits[i & 1], self.d_labels[i & 1], self.ctx.stream.cuda_stream)
+
+    def snapshot(self):
+        return [(self.d_logits[k].cpu().numpy(), self.d_labels[k].cpu().numpy().view(np.uint32)) for k in range(2)]
+
+
+def int_alu_peak_ops(sm_max_mhz):
+    """Integer-ALU roofline of the CNN front-end: the dot-product unit issues one IDP.4A warp instruction per 2 cycles per SM
+    sub-partition (tools/alu_rates.cu, profiles/r1_micro_alu_rates.txt: 2.00 cycles) = 64 lanes/clk/SM x 4 MAC x 2 ops, 148 SMs,
+    at the maximum SM clock.  (conv2/conv3 take int16/int32 activations and can only use IDP.2A / IMAD = 2 / 1 MAC per lane.)"""
+    return 148 * 64 * 8 * sm_max_mhz * 1e6
+
+
+def run_config(ctx, name, batch, steps, warmup, args, check_parity=True, host_imgs=None):
+    """One BASELINE config: device-timed plain launches, its roofline, full-batch parity against the oracle (rank 0)."""
+    from bitnetmcu_b200 import _lib
+    from bitnetmcu_b200.engine import Engine
+    model = load_model(name)
+    eng = Engine(model, device=ctx.local_rank)
+    n, C = batch, eng.n_classes
+    if host_imgs is None or host_imgs.shape[0] != n:
+        host_imgs = synth_images(n, eng.img_bytes, 4321 + ctx.rank, args.dist)
+    db = DeviceBatch(ctx, eng, host_imgs)
+    eng.set_option(_lib.OPT_LAUNCH_OVERLAP, 0)
+    ms, _ = ctx.timed_steps(db.step, steps, warmup)
+    value = ctx.world * n / (ms * 1e-3)
+    peak_gbs, peak_src, sm_max = measured_peaks()
+    bytes_per_image = eng.img_bytes + 4 * C
+    hbm_ach = bytes_per_image * n / (ms * 1e-3) / 1e9
+    cnn = model.model_class == 1
+    if cnn:
+        ops = 2.0 * model.macs_per_image * n / (ms * 1e-3)
+        peak_ops = int_alu_peak_ops(sm_max)
+        roof = {"bound": "int_alu", "achieved": ops / 1e12, "peak": peak_ops / 1e12, "unit": "Top/s", "frac": ops / peak_ops,
+                "peak_source": f"IDP.4A issue rate (1 warp instruction / 2 cycles / SM sub-partition, tools/alu_rates.cu) x 148 SMs x {sm_max:.0f} MHz",
+                "macs_per_image": model.macs_per_image, "hbm_frac": hbm_ach / peak_gbs, "traffic": None}
+    else:
+        roof = {"bound": "hbm", "achieved": hbm_ach, "peak": peak_gbs, "unit": "GB/s", "frac": hbm_ach / peak_gbs,
+                "peak_source": peak_src, "algorithmic_bytes_per_image": bytes_per_image, "traffic": traffic_for(name, n)}
+    out = {"name": name, "workload": workload_name(name, model, n), "value": value, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "warmup": warmup, "gpu_launches_per_step": eng.launch_count(n), "launch_semantics": "plain launches",
+           "path": "tcgen05" if eng.active_path == _lib.PATH_TCGEN05 else "layers", "roofline": roof}
+    if cnn:
+        out["cnn_frontend"] = {0: "auto (tensor cores when covered)", 1: "CUDA cores", 2: "tensor cores"}.get(int(eng.lib.bnm_model_get_option(eng.handle, _lib.OPT_CNN_FRONTEND)))
+    if check_parity and ctx.rank == 0:
+        try:
+            from oracle.oracle import Oracle
+            got_l, got_b = db.snapshot()[0]
+            t0 = time.perf_counter()
+            ns = n if n <= (1 << 20) else (1 << 18)
+            oo, ol = Oracle().infer(model, host_imgs[:ns], threads=checker_threads())
+            ok = bool(zlib.crc32(got_l[:ns].tobytes()) == zlib.crc32(oo.tobytes()) and np.array_equal(got_b[:ns], ol))
+            out["parity"] = ok
+            out["parity_check"] = (f"logits CRC-32 + labels of {'the full batch' if ns == n else 'the first %d images' % ns} of the timed launches "
+                                   f"vs the oracle ({time.perf_counter() - t0:.1f} s of CPU)")
+        except Exception as ex:
+            out["parity"] = f"oracle unavailable: {ex}"
+    eng.close()
+    del db
+    ctx.torch.cuda.empty_cache()
+    return out
+
+
+_TRAFFIC = None
+
+
+def traffic_for(name, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/traffic.json);
+    not re-measured inside a bench run (nothing printed under a profiler is a bench value)."""
+    global _TRAFFIC
+    if _TRAFFIC is None:
+        try:
+            _TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            _TRAFFIC = {}
+    return _TRAFFIC.get(f"{name}:{n}")
+
+
+def latency_batch1(model_name="fc", calls=10000):
+    """Single-image latency of the drop-in: host/bitnetmcu_b200_latency.c (plain C, gcc) dlopen()s a DLL and calls its exported
+    Inference() `calls` times over the ten reference digits -- once for the gcc-built shim of THIS library (host/bitnetmcu_b200_dll.c +
+    a header written from the fixture model), once for the reference's own DLL (oracle/_ref, when it travelled)."""
+    from bitnetmcu_b200 import _lib
+    from bitnetmcu_b200.pack import write_header
+    out = {"calls": calls, "model": model_name}
+    tmp = tempfile.mkdtemp(prefix="bnm_lat_")
+    try:
+        m = load_model(model_name)
+        write_header(m, os.path.join(tmp, "BitNetMCU_model.h"))
+        libdir = os.path.dirname(_lib.LIB_PATH)
+        dll = os.path.join(tmp, "Bitnet_inf.dll")
+        exe = os.path.join(tmp, "latency")
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-D_DLL", "-o", dll, os.path.join(ROOT, "host", "bitnetmcu_b200_dll.c"), "-I" + tmp,
+                        "-I" + os.path.join(ROOT, "include"), "-L" + libdir, "-lbitnetmcu_b200", "-Wl,-rpath," + libdir], check=True, capture_output=True)
+        subprocess.run(["gcc", "-O2", "-o", exe, os.path.join(ROOT, "host", "bitnetmcu_b200_latency.c"), "-ldl"], check=True, capture_output=True)
+        d = np.load(os.path.join(ROOT, "tests", "golden", "digits.npz"))
+        d["images"].astype(np.int8).tofile(os.path.join(tmp, "digits.bin"))
+        want = ",".join(str(int(v)) for v in d["labels"])
+
+        def run(path):
+            r = subprocess.run([exe, path, os.path.join(tmp, "digits.bin"), str(calls)], capture_output=True, text=True, timeout=300)
+            return json.loads(r.stdout.strip().splitlines()[-1])
+        ours = run(dll)
+        out["ours_us"] = ours["us_per_call"]
+        out["ours_labels_ok"] = ours["labels"] == want
+        ref = os.path.join(ROOT, "oracle", "_ref", f"Bitnet_inf_{model_name}.so")
+        if os.path.exists(ref):
+            r = run(ref)
+            out["reference_us"] = r["us_per_call"]
+            out["reference_labels_ok"] = r["labels"] == want
+        else:
+            out["reference_us"] = None
+        out["note"] = "one image per call through the exported Inference(): H2D + launch + D2H + sync per call (ours), one CPU core (reference)"
+    except Exception as ex:
+        out["error"] = str(ex)[:300]
+    return out
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -224,145 +453,96 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 20, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE.json configs)")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--sustain-seconds", type=float, default=1.0)
     ap.add_argument("--path", default="auto", choices=["auto", "layers", "tcgen05"])
     ap.add_argument("--dist", default="uniform", choices=["uniform", "mnist"], help="synthetic image distribution (SURVEY.md 8d config 2)")
-    ap.add_argument("--overlap", type=int, default=2, choices=[0, 1, 2],
-                    help="BNM_OPT_LAUNCH_OVERLAP: 0 plain launches, 1 dependent launch (prologue overlap only), "
-                         "2 consecutive launches declared independent (the bench double-buffers inputs AND outputs); "
-                         "the plain-launch figure is always reported next to the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    import torch
-    from bitnetmcu_b200 import _lib, dist as bdist
+    from bitnetmcu_b200 import _lib
     from bitnetmcu_b200.engine import Engine
-
-    rank, local_rank, world = bdist.env_rank_world()
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's INFO log: stderr, not stdout (see claim_stdout)
-        bdist.init_process_group("nccl")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    import torch.distributed as tdist
-
-    def barrier():
-        if world > 1:
-            tdist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-        return float(t.item())
-
+    ctx = Ctx()
+    torch, rank, world = ctx.torch, ctx.rank, ctx.world
     model = load_model(args.model)
     path = {"auto": _lib.PATH_AUTO, "layers": _lib.PATH_LAYERS, "tcgen05": _lib.PATH_TCGEN05}[args.path]
-    eng = Engine(model, device=local_rank, path=path)
-    n = args.batch
-    C = eng.n_classes
+    eng = Engine(model, device=ctx.local_rank, path=path)
+    n, C = args.batch, eng.n_classes
 
-    # ---- device-resident inputs: two buffers alternated, each (n x img_bytes = 268 MB at 1M) larger than the 126 MB L2
+    # ---- device-resident inputs, larger than L2, alternated per step
     host_imgs = synth_images(n, eng.img_bytes, 1234 + rank, args.dist)
-    d_in = [torch.from_numpy(host_imgs).to(dev), torch.from_numpy(np.ascontiguousarray(host_imgs[::-1])).to(dev)]
-    # outputs double-buffered too: step i reads d_in[i & 1] and writes d_logits[i & 1] / d_labels[i & 1], so consecutive
-    # launches touch disjoint buffers -- the promise BNM_OPT_LAUNCH_OVERLAP = 2 asks for
-    d_logits = [torch.empty((n, C), dtype=torch.int32, device=dev) for _ in range(2)]
-    d_labels = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
-    stream = torch.cuda.current_stream(dev)
-    eng.set_option(_lib.OPT_LAUNCH_OVERLAP, args.overlap)
+    db = DeviceBatch(ctx, eng, host_imgs)
 
-    def step(i):
-        eng.infer_device(d_in[i & 1], d_logits[i & 1], d_labels[i & 1], stream.cuda_stream)
-
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    sampler.start()
-    time.sleep(0.25)
-    # ---- timed region: exactly K steps, CUDA events on the launching stream, barrier + synchronize on both sides
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    ev1.record(stream)
-    barrier()
-    t_wall1 = time.perf_counter()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    # keep the GPU under load a little longer so that the 100 ms clock sampler sees the loaded state
-    t_hold = time.perf_counter()
-    i = 0
-    while time.perf_counter() - t_hold < 0.6:
-        step(i); i += 1
-        if i % 50 == 0:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
-    # results of back-to-back (overlapped) launches, kept for the full-batch parity check below
-    snap = [(d_logits[k].cpu().numpy(), d_labels[k].cpu().numpy()) for k in range(2)]
-    clocks = sampler.stop(t_wall0, time.perf_counter())
-    ms_per_step = ms_total / args.steps
+    # ---- headline: K steps, plain launches (ordinary stream semantics)
+    eng.set_option(_lib.OPT_LAUNCH_OVERLAP, 0)
+    ms_per_step, local_ms = ctx.timed_steps(db.step, args.steps, args.warmup)
     value = world * n / (ms_per_step * 1e-3)
+    snap_plain = db.snapshot()
     launches = args.steps * eng.launch_count(n)
 
-    # ---- dominant kernel duration.  On the fused FC path a step IS one launch of fc_chain_kernel, so its average launch
-    # duration over the timed region is ms_total / steps (CUDA events on the launching stream, back-to-back launches; with
-    # launch overlap the ragged end of one launch runs under the start of the next, which is the point).  An isolated
-    # figure (one event pair per launch: no overlap, includes the event/launch gap) is reported next to it.
+    # ---- the same steps with consecutive launches declared independent (BNM_OPT_LAUNCH_OVERLAP = 2)
+    eng.set_option(_lib.OPT_LAUNCH_OVERLAP, 2)
+    ms_overlap, _ = ctx.timed_steps(db.step, args.steps, 3)
+    snap_overlap = db.snapshot()
+    eng.set_option(_lib.OPT_LAUNCH_OVERLAP, 0)
+
+    # ---- sustained: >= sustain_seconds of back-to-back plain launches, clocks sampled over exactly this region
+    for i in range(3):
+        db.step(i)
+    ctx.barrier()
+    sampler = ClockSampler(ClockSampler.device_selector(ctx.local_rank))
+    sampler.start()
+    time.sleep(0.3)
+    ctx.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_s0 = time.perf_counter()
+    s0.record(ctx.stream)
+    n_sus = 0
+    while True:
+        for _ in range(64):
+            db.step(n_sus); n_sus += 1
+        torch.cuda.synchronize()
+        if time.perf_counter() - t_s0 >= args.sustain_seconds:
+            break
+    s1.record(ctx.stream)
+    torch.cuda.synchronize()
+    t_s1 = time.perf_counter()
+    sus_ms = ctx.max_over_ranks(s0.elapsed_time(s1))
+    clocks = sampler.stop(t_s0, t_s1, f"the value_sustained loop ({n_sus} back-to-back plain launches, {sus_ms / 1e3:.2f} s), which runs the same "
+                                      "kernel on the same buffers right after the timed steps (the timed region itself is ~1 ms, below the 100 ms sampling period)")
+    sustained = {"value": world * n * n_sus / (sus_ms * 1e-3), "unit": UNIT, "seconds": sus_ms / 1e3, "launches": n_sus,
+                 "ms_per_step": sus_ms / n_sus, "note": "a host synchronise every 64 launches is inside the region"}
+
+    # ---- one launch timed alone with its own event pair (no overlap with neighbours, includes the event/launch gap)
     durs = []
     for i in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream); step(i); b.record(stream)
+        a.record(ctx.stream); db.step(i); b.record(ctx.stream)
         durs.append((a, b))
     torch.cuda.synchronize()
     kernel_ms_isolated = statistics.mean(a.elapsed_time(b) for a, b in durs)
-    # ---- the same K steps with plain launches (BNM_OPT_LAUNCH_OVERLAP = 0), for reference next to the headline
-    plain_ms = None
-    if args.overlap != 0:
-        eng.set_option(_lib.OPT_LAUNCH_OVERLAP, 0)
-        for i in range(3):
-            step(i)
-        barrier()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(stream)
-        for i in range(args.steps):
-            step(i)
-        p1.record(stream)
-        barrier()
-        plain_ms = max_over_ranks(p0.elapsed_time(p1)) / args.steps
-        eng.set_option(_lib.OPT_LAUNCH_OVERLAP, args.overlap)
-    single_kernel_step = eng.launch_count(n) == 1
-    local_ms_per_step = ev0.elapsed_time(ev1) / args.steps
-    kernel_ms = local_ms_per_step if single_kernel_step else kernel_ms_isolated
-    bytes_per_image = eng.img_bytes + 4 * C          # SURVEY.md 8d: 256 B read + 10 x int32 written = 296 B (labels +4 B not counted)
-    achieved = bytes_per_image * n / (kernel_ms * 1e-3) / 1e9
-    peak, peak_src = measured_peak_gbs()
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")     # dram__bytes_read+write per launch from the committed ncu capture
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(f"{args.model}:{n}")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "fc_chain_kernel" if eng.active_path == _lib.PATH_TCGEN05 else "layer kernels",
-                "kernel_ms": kernel_ms, "kernel_ms_isolated_launch": kernel_ms_isolated,
-                "kernel_ms_plain_launches": plain_ms,
-                "frac_plain_launches": (bytes_per_image * n / (plain_ms * 1e-3) / 1e9 / peak) if (plain_ms and single_kernel_step) else None,
-                "algorithmic_bytes_per_image": bytes_per_image, "peak_source": peak_src}
 
-    # ---- sanity: the timed path is bit-exact on a sample (oracle = checker only, outside every timed region)
+    single_kernel_step = eng.launch_count(n) == 1
+    kernel_ms = local_ms if single_kernel_step else kernel_ms_isolated
+    bytes_per_image = eng.img_bytes + 4 * C          # SURVEY.md 8d: 256 B read + 10 x int32 written = 296 B (labels +4 B not counted)
+    peak, peak_src, _ = measured_peaks()
+    gbs = lambda ms: bytes_per_image * n / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": gbs(kernel_ms), "peak": peak, "unit": "GB/s", "frac": gbs(kernel_ms) / peak,
+                "traffic": traffic_for(args.model, n), "kernel": "fc_chain_kernel" if eng.active_path == _lib.PATH_TCGEN05 else "layer kernels",
+                "kernel_ms": kernel_ms, "kernel_ms_isolated_launch": kernel_ms_isolated,
+                "frac_overlapped_launches": gbs(ms_overlap) / peak if single_kernel_step else None,
+                "frac_sustained": gbs(sus_ms / n_sus) / peak if single_kernel_step else None,
+                "algorithmic_bytes_per_image": bytes_per_image, "peak_source": peak_src,
+                "launch_semantics": "frac = plain launches (ordinary stream semantics)"}
+
+    # ---- e2e through the C ABI with pinned host buffers + parity of everything timed above (oracle = checker only)
     parity = None
     e2e = None
     if not args.no_e2e:
         lib = _lib.load()
-        import ctypes as Ct
         nb_in, nb_log, nb_lab = n * eng.img_bytes, n * C * 4, n * 4
         p_in, p_log, p_lab = lib.bnm_host_alloc(nb_in), lib.bnm_host_alloc(nb_log), lib.bnm_host_alloc(nb_lab)
         h_in = np.ctypeslib.as_array((Ct.c_int8 * nb_in).from_address(p_in)).reshape(n, eng.img_bytes)
@@ -372,78 +552,86 @@ def main():
         eng.set_option(_lib.OPT_CHUNK_IMAGES, 1 << 17)
         for _ in range(3):
             eng.infer(h_in, out_logits=h_log, out_labels=h_lab)
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             eng.infer(h_in, out_logits=h_log, out_labels=h_lab)
         torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": nb_in, "d2h_bytes_per_step": nb_log + nb_lab,
                "ms_per_step": 1e3 * dt / args.steps, "api": "bnm_infer_batch (pinned host buffers, 3-stream chunk pipeline)"}
-        # parity of the e2e result against the checker on a slice
         try:
             from oracle.oracle import Oracle
             ns = min(n, 1 << 16)
-            oo, ol = Oracle().infer(model, host_imgs[:ns])
+            oo, ol = Oracle().infer(model, host_imgs[:ns], threads=checker_threads())
             parity = bool(np.array_equal(h_log[:ns], oo) and np.array_equal(h_lab[:ns], ol))
-            # ... and the device path's results from the overlapped launches, the whole batch, both buffers (buffer 1 holds
-            # the images in reverse order), against the e2e result that was just checked
-            parity = parity and bool(np.array_equal(snap[0][0], h_log) and np.array_equal(snap[0][1].view(np.uint32), h_lab)
-                                     and np.array_equal(snap[1][0], h_log[::-1]) and np.array_equal(snap[1][1].view(np.uint32), h_lab[::-1]))
+            # ... and the device path's results, the whole batch, both buffers (buffer 1 holds the images in reverse order), plain
+            # and overlapped launches, against the e2e result that was just checked
+            for snap in (snap_plain, snap_overlap):
+                parity = parity and bool(np.array_equal(snap[0][0], h_log) and np.array_equal(snap[0][1], h_lab)
+                                         and np.array_equal(snap[1][0], h_log[::-1]) and np.array_equal(snap[1][1], h_lab[::-1]))
         except Exception as ex:  # the checker being unavailable must not hide the measurement
             parity = f"oracle unavailable: {ex}"
         lib.bnm_host_free(p_in); lib.bnm_host_free(p_log); lib.bnm_host_free(p_lab)
 
-    # ---- N > 1: the optional result exchange, timed separately -- `value` keeps the logits sharded.  A GPU
-    # ingests <= ~900 GB/s over NVLink, so gathering all logits onto every rank caps the box near 22 G images/s whatever
-    # the kernels do; labels (4 B/image) are the exchange that scales.
+    # ---- N > 1: the result exchange, timed separately -- `value` keeps the logits sharded
     gather = None
     if world > 1:
-        all_lab = torch.empty(n * world, dtype=torch.int32, device=dev)
-        all_log = torch.empty((n * world, C), dtype=torch.int32, device=dev)
-        def timed(fn, reps=5):
-            fn(); barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(reps):
-                fn()
-            b.record(stream); barrier()
-            return max_over_ranks(a.elapsed_time(b) / reps)
-        lab_ms = timed(lambda: tdist.all_gather_into_tensor(all_lab, d_labels[0]))
-        log_ms = timed(lambda: tdist.all_gather_into_tensor(all_log, d_logits[0]))
-        ok = bool(torch.equal(all_lab[rank * n:(rank + 1) * n], d_labels[0]) and torch.equal(all_log[rank * n:(rank + 1) * n], d_logits[0]))
-        gather = {"all_gather_labels_ms": lab_ms, "all_gather_logits_ms": log_ms, "backend": "nccl", "own_shard_intact": ok,
-                  "value_with_label_all_gather": world * n / ((ms_per_step + lab_ms) * 1e-3),
-                  "value_with_logits_all_gather": world * n / ((ms_per_step + log_ms) * 1e-3),
-                  "note": "serial compute + exchange per step; the headline value leaves results sharded in each GPU's HBM"}
-        del all_lab, all_log
+        try:
+            from bitnetmcu_b200 import gather as bgather
+            gather = bgather.bench_gathers(ctx, eng, db, ms_per_step)
+        except Exception as ex:
+            gather = {"error": str(ex)[:300]}
+
+    del db
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configs
+    configs = None
+    if not args.no_configs:
+        configs = []
+        shared = None
+        for name, batch in EXTRA_CONFIGS:
+            try:
+                if shared is None or shared.shape[0] != batch:
+                    shared = host_imgs if batch == n else synth_images(batch, 256, 977 + rank, args.dist)
+                t0 = time.perf_counter()
+                c = run_config(ctx, name, batch, steps=10 if batch <= (1 << 20) else 5, warmup=3, args=args, host_imgs=shared)
+                log(f"config {name}@{batch}: {c['value'] / 1e9:.3f} G img/s, frac {c['roofline']['frac']:.3f}, parity {c.get('parity')}, {time.perf_counter() - t0:.1f} s")
+                configs.append(c)
+            except Exception as ex:
+                configs.append({"name": name, "error": str(ex)[:300]})
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            cpu_base, _, _, _ = cpu_reference_rate(model, host_imgs, budget_s=1.0, reps=3)
-        except Exception as ex:
-            cpu_base = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(ex)}
+    latency = None
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            try:
+                cpu_base, _, _, _ = cpu_reference_rate(model, host_imgs, budget_s=1.0, reps=3)
+            except Exception as ex:
+                cpu_base = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(ex)}
+        if not args.no_latency:
+            latency = latency_batch1(args.model)
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8", "data": "synthetic" if args.dist == "uniform" else "synthetic (MNIST-like value profile)",
-            "config": {"workload": workload_name(args, model), "batch_per_gpu": n, "global_batch": n * world,
+            "config": {"workload": workload_name(args.model, model, n), "batch_per_gpu": n, "global_batch": n * world,
                        "parallelism": f"dp{world} (batch sharded, logits stay sharded; no data-path collective)",
                        "l2": "inputs larger than L2: two 268 MB image buffers alternated per step, TMA evict-first loads",
                        "path": "tcgen05" if eng.active_path == _lib.PATH_TCGEN05 else "layers",
-                       "launch_overlap": {0: "none", 1: "programmatic dependent launch, inputs read after the previous kernel completed",
-                                          2: "programmatic dependent launch, consecutive steps independent (inputs and outputs double-buffered)"}[args.overlap]},
+                       "launch_semantics": "plain launches (BNM_OPT_LAUNCH_OVERLAP = 0): ordinary stream semantics"},
+            "value_overlapped_launches": world * n / (ms_overlap * 1e-3),
+            "value_sustained": sustained,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
-            "parity_vs_oracle_sample": parity, "gather": gather,
-            "value_plain_launches": (world * n / (plain_ms * 1e-3)) if plain_ms else None,
+            "parity_vs_oracle_sample": parity, "gather": gather, "configs": configs, "latency_us_batch1": latency,
         }
         print(json.dumps(out), file=RESULT_OUT, flush=True)
     eng.close()
     if world > 1:
-        tdist.destroy_process_group()
+        ctx.tdist.destroy_process_group()
 
 
 if __name__ == "__main__":

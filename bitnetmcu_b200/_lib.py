@@ -19,15 +19,27 @@ EXPORTED = [
     "bnm_infer_batch", "bnm_infer_batch_device", "bnm_infer_launch_count", "bnm_host_alloc", "bnm_host_free",
     "bnm_processfclayer_batch", "bnm_relunorm_batch", "bnm_conv33relu_batch", "bnm_maxpool22_batch",
     "bnm_quantize_images", "bnm_quantize_images_device",
+    "bnm_infer_batch_device_gather", "bnm_device_alloc", "bnm_device_free", "bnm_ipc_export", "bnm_ipc_open", "bnm_ipc_close",
+    "bnm_enable_peer_access",
 ]
 
 PATH_AUTO, PATH_LAYERS, PATH_TCGEN05 = 0, 1, 2
-OPT_PATH, OPT_NF4_EXTENSION, OPT_CHUNK_IMAGES, OPT_LAUNCH_OVERLAP = 1, 2, 3, 4
+OPT_PATH, OPT_NF4_EXTENSION, OPT_CHUNK_IMAGES, OPT_LAUNCH_OVERLAP, OPT_CNN_FRONTEND = 1, 2, 3, 4, 5
+CNN_AUTO, CNN_CUDA_CORES, CNN_TENSOR_CORES = 0, 1, 2
 
 
 class BnmLayer(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("bitperweight", C.c_int32), ("n_in", C.c_uint32), ("n_out", C.c_uint32),
                 ("in_channels", C.c_uint32), ("groups", C.c_uint32), ("weights", C.c_void_p), ("weight_bytes", C.c_size_t)]
+
+
+MAX_GATHER_DST = 8
+
+
+class BnmGather(C.Structure):
+    """bnm_gather (include/bitnetmcu_b200.h): destinations of the fused result exchange."""
+    _fields_ = [("n_labels_dst", C.c_uint32), ("n_logits_dst", C.c_uint32), ("labels_dst", C.c_void_p * MAX_GATHER_DST),
+                ("logits_dst", C.c_void_p * MAX_GATHER_DST), ("row_offset", C.c_size_t)]
 
 
 _lib = None
@@ -61,6 +73,10 @@ def load() -> C.CDLL:
         "bnm_maxpool22_batch": (C.c_int, [vp, u32, vp, sz]),
         "bnm_quantize_images": (C.c_int, [vp, sz, u32, vp]),
         "bnm_quantize_images_device": (C.c_int, [vp, sz, u32, vp, vp]),
+        "bnm_infer_batch_device_gather": (C.c_int, [vp, vp, sz, vp, vp, C.POINTER(BnmGather), vp]),
+        "bnm_device_alloc": (C.c_int, [C.c_int, sz, C.POINTER(vp)]), "bnm_device_free": (None, [vp]),
+        "bnm_ipc_export": (C.c_int, [vp, vp]), "bnm_ipc_open": (C.c_int, [C.c_int, vp, C.POINTER(vp)]), "bnm_ipc_close": (C.c_int, [vp]),
+        "bnm_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
         "ReLUNorm": (u32, [vp, vp, u32]),
         "processfclayer": (None, [vp, vp, i32, u32, u32, vp]),
         "processconv33ReLU": (vp, [vp, vp, u32, u32, vp]),

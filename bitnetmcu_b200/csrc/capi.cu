@@ -67,6 +67,8 @@ struct bnm_model {
     int nf4_ext = 0;
     size_t chunk_images = 1 << 16;   // host pipeline chunk
     int launch_overlap = 0;
+    int cnn_frontend = 0;            // BNM_OPT_CNN_FRONTEND
+    int *d_err = nullptr;            // error word of the bounded device-side waits
     // fused plan
     FcChainPlan *plan = nullptr;
     std::string plan_err;
@@ -79,7 +81,13 @@ struct bnm_model {
     // host pipeline
     PipeSlot slots[3];
     size_t slot_n = 0;
+    // small-batch path of bnm_infer_batch (the reference's own calling pattern: one image per Inference() call,
+    // test_inference.py:146-150): pinned staging buffers, one stream, one synchronisation
+    int8_t *small_h_in = nullptr, *small_d_in = nullptr;     // [kSmallBatch][img_bytes]
+    int32_t *small_h_out = nullptr, *small_d_out = nullptr;  // logits [n][n_classes] then labels [n]
+    int small_zero_copy = 0;   // 0: H2D + D2H copies; 1: the kernel writes results straight into mapped pinned host memory; 2: ... and reads the images from it
 };
+static const size_t kSmallBatch = 1024;
 
 static void free_fc_dev(bnm_model *m) {
     for (auto &L : m->fc) {
@@ -174,6 +182,7 @@ static int ensure_scratch(bnm_model *m, size_t n) {
     return 0;
 }
 
+static int require_device_index(int device);
 extern "C" int bnm_version(void) { return BNM_VERSION; }
 extern "C" const char *bnm_last_error(void) { return g_err.c_str(); }
 extern "C" int bnm_device_count(void) {
@@ -253,7 +262,9 @@ extern "C" int bnm_model_create(int model_class, const bnm_layer *layers, uint32
     }
     if (rc == 0 && model_class == BNM_MODEL_FCMNIST && !front.empty()) rc = fail(BNM_E_ARG, "MODEL_FCMNIST with conv/pool layers");
     if (rc == 0) rc = build_fc_dev(m);
+    if (rc == 0 && (cudaMalloc(&m->d_err, sizeof(int)) != cudaSuccess || cudaMemset(m->d_err, 0, sizeof(int)) != cudaSuccess)) rc = fail(BNM_E_CUDA, "cudaMalloc failed");
     if (rc == 0) {
+        if (const char *e = getenv("BNM_CNN_FRONTEND")) m->cnn_frontend = std::max(0, std::min(2, atoi(e)));   // development override, read once per model
         for (auto &s : m->slots)
             if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(BNM_E_CUDA, "cudaStreamCreate failed"); break; }
     }
@@ -291,6 +302,11 @@ extern "C" void bnm_model_destroy(bnm_model *m) {
     cudaFree(m->d_act[0]);
     cudaFree(m->d_act[1]);
     cudaFree(m->d_feat);
+    cudaFree(m->d_err);
+    cudaFree(m->small_d_in);
+    cudaFree(m->small_d_out);
+    if (m->small_h_in) cudaFreeHost(m->small_h_in);
+    if (m->small_h_out) cudaFreeHost(m->small_h_out);
     for (auto &s : m->slots) {
         cudaFree(s.d_images);
         cudaFree(s.d_logits);
@@ -327,6 +343,12 @@ extern "C" int bnm_model_set_option(bnm_model *m, int option, int64_t value) {
         if (value < 128) return fail(BNM_E_ARG, "chunk must be >= 128 images");
         m->chunk_images = (size_t)value;
         return 0;
+    case BNM_OPT_CNN_FRONTEND:
+        if (value < 0 || value > 2) return fail(BNM_E_ARG, "CNN front-end must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
+        if (value == 2 && !(m->model_class == BNM_MODEL_CNNMNIST && cnn_frontend_tc_supported(m->channels, m->xy0)))
+            return fail(BNM_E_UNSUPPORTED, "tensor-core CNN front-end needs a 16x16 CNN model with a multiple of 16 (<= 128) channels");
+        m->cnn_frontend = (int)value;
+        return 0;
     case BNM_OPT_LAUNCH_OVERLAP:
         if (value < 0 || value > 2) return fail(BNM_E_ARG, "launch overlap mode must be 0, 1 or 2");
         m->launch_overlap = (int)value;
@@ -343,6 +365,7 @@ extern "C" int64_t bnm_model_get_option(const bnm_model *m, int option) {
     case BNM_OPT_NF4_EXTENSION: return m->nf4_ext;
     case BNM_OPT_CHUNK_IMAGES: return (int64_t)m->chunk_images;
     case BNM_OPT_LAUNCH_OVERLAP: return m->launch_overlap;
+    case BNM_OPT_CNN_FRONTEND: return m->cnn_frontend;
     default: return -1;
     }
 }
@@ -378,9 +401,10 @@ static int run_fc_layers(bnm_model *m, const int8_t *in, uint32_t in_stride, siz
 // CNN front-end into m->d_feat (int8 [n][feat_stride])
 static int run_cnn_front(bnm_model *m, const int8_t *images, size_t n, cudaStream_t st) {
     if (launch_cnn_frontend(images, m->d_conv[0], m->d_conv[1], m->d_conv[2], m->channels, m->xy0, m->d_feat, m->feat_stride, n,
-                            m->sm_count, st))
+                            m->sm_count, m->cnn_frontend, m->d_err, st))
         return 0;
-    return fail(BNM_E_UNSUPPORTED, "CNN geometry %ux%u not supported (the reference hard-codes 16x16, dll.c:68)", m->xy0, m->xy0);
+    return fail(BNM_E_UNSUPPORTED, "CNN front-end: %u channels at %ux%u not supported by the selected kernel (the reference hard-codes 16x16, dll.c:68)",
+                m->channels, m->xy0, m->xy0);
 }
 
 extern "C" int bnm_infer_launch_count(const bnm_model *m, size_t n) {
@@ -394,7 +418,7 @@ extern "C" int bnm_infer_launch_count(const bnm_model *m, size_t n) {
     return (int)(chunks * per);
 }
 
-extern "C" int bnm_infer_batch_device(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels, void *stream) {
+static int infer_device_impl(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels, const GatherDst *gather, void *stream) {
     if (!m || (n && (!images || !logits))) return fail(BNM_E_ARG, "bnm_infer_batch_device: null argument");
     if (n == 0) return 0;
     if (((uintptr_t)images | (uintptr_t)logits) & 15) return fail(BNM_E_ARG, "device buffers must be 16-byte aligned");
@@ -402,8 +426,9 @@ extern "C" int bnm_infer_batch_device(bnm_model *m, const int8_t *images, size_t
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool fused = bnm_model_active_path(m) == BNM_PATH_TCGEN05;
     const bool cnn = m->model_class == BNM_MODEL_CNNMNIST;
+    if (gather && !fused) return fail(BNM_E_UNSUPPORTED, "the fused result exchange needs the tcgen05 path (model: %s)", m->plan_err.c_str());
     if (fused && !cnn) {
-        int rc = fc_chain_launch(m->plan, images, n, logits, labels, st);
+        int rc = fc_chain_launch(m->plan, images, n, logits, labels, gather, st);
         return rc ? fail(BNM_E_CUDA, "fused FC kernel launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())) : 0;
     }
     const size_t chunk = std::min(n, kLayeredChunk);
@@ -423,7 +448,9 @@ extern "C" int bnm_infer_batch_device(bnm_model *m, const int8_t *images, size_t
             fc_stride = m->feat_stride;
         }
         if (fused) {
-            rc = fc_chain_launch(m->plan, fc_in, nb, lg, lb, st);
+            GatherDst gchunk;
+            if (gather) { gchunk = *gather; gchunk.row_offset += b; }
+            rc = fc_chain_launch(m->plan, fc_in, nb, lg, lb, gather ? &gchunk : nullptr, st);
             if (rc) return fail(BNM_E_CUDA, "fused FC kernel launch failed (%d)", rc);
         } else {
             rc = run_fc_layers(m, fc_in, fc_stride, nb, lg, lb, st);
@@ -434,13 +461,107 @@ extern "C" int bnm_infer_batch_device(bnm_model *m, const int8_t *images, size_t
     return e == cudaSuccess ? 0 : fail(BNM_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
 }
 
+extern "C" int bnm_infer_batch_device(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels, void *stream) {
+    return infer_device_impl(m, images, n, logits, labels, nullptr, stream);
+}
+
+extern "C" int bnm_infer_batch_device_gather(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels,
+                                             const bnm_gather *gather, void *stream) {
+    static_assert(sizeof(bnm_gather) == sizeof(GatherDst), "bnm_gather and GatherDst must share their layout");
+    if (gather && (gather->n_labels_dst > BNM_MAX_GATHER_DST || gather->n_logits_dst > BNM_MAX_GATHER_DST))
+        return fail(BNM_E_ARG, "at most %d gather destinations", BNM_MAX_GATHER_DST);
+    if (gather)
+        for (uint32_t d = 0; d < gather->n_logits_dst; d++)
+            if ((uintptr_t)gather->logits_dst[d] & 7) return fail(BNM_E_ARG, "gather logits buffers must be 8-byte aligned");
+    return infer_device_impl(m, images, n, logits, labels, reinterpret_cast<const GatherDst *>(gather), stream);
+}
+
+// -----------------------------------------------------------------------------------------------
+// peer memory plumbing for the fused result exchange: cudaMalloc'd buffers exported / opened through CUDA IPC
+// -----------------------------------------------------------------------------------------------
+extern "C" int bnm_device_alloc(int device, size_t bytes, void **out) {
+    if (!out) return fail(BNM_E_ARG, "bnm_device_alloc: null argument");
+    *out = nullptr;
+    if (int rc = require_device_index(device)) return rc;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaMalloc(out, bytes ? bytes : 16));
+    return 0;
+}
+extern "C" void bnm_device_free(void *p) { if (p) cudaFree(p); }
+extern "C" int bnm_ipc_export(const void *dev_ptr, void *handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!dev_ptr || !handle64) return fail(BNM_E_ARG, "bnm_ipc_export: null argument");
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+extern "C" int bnm_ipc_open(int device, const void *handle64, void **out) {
+    if (!handle64 || !out) return fail(BNM_E_ARG, "bnm_ipc_open: null argument");
+    *out = nullptr;
+    if (int rc = require_device_index(device)) return rc;
+    CU_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int bnm_ipc_close(void *p) {
+    if (!p) return 0;
+    CU_TRY(cudaIpcCloseMemHandle(p));
+    return 0;
+}
+// same-process multi-GPU callers: let `device` read / write memory of `peer` directly
+extern "C" int bnm_enable_peer_access(int device, int peer) {
+    if (int rc = require_device_index(device)) return rc;
+    if (int rc = require_device_index(peer)) return rc;
+    if (device == peer) return 0;
+    int can = 0;
+    CU_TRY(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return fail(BNM_E_UNSUPPORTED, "device %d cannot access device %d (no P2P path)", device, peer);
+    CU_TRY(cudaSetDevice(device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    CU_TRY(e);
+    return 0;
+}
+
 // -----------------------------------------------------------------------------------------------
 // batched inference, host pointers: chunks round-robin over three streams so H2D, kernels and D2H overlap
 // -----------------------------------------------------------------------------------------------
+// n <= kSmallBatch images: staging buffers allocated once, one stream, one synchronisation per call
+static int infer_small(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels) {
+    const size_t in_bytes = kSmallBatch * (size_t)m->img_bytes, out_ints = kSmallBatch * ((size_t)m->n_classes + 1);
+    if (!m->small_h_in) {
+        if (const char *e = getenv("BNM_SMALL_ZC")) m->small_zero_copy = std::max(0, std::min(2, atoi(e)));   // development knob, read once per model
+        CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&m->small_h_in), in_bytes, cudaHostAllocMapped));
+        CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&m->small_h_out), out_ints * 4, cudaHostAllocMapped));
+        CU_TRY(cudaMalloc(&m->small_d_in, in_bytes));
+        CU_TRY(cudaMalloc(&m->small_d_out, out_ints * 4));
+    }
+    cudaStream_t st = m->slots[0].stream;
+    memcpy(m->small_h_in, images, n * (size_t)m->img_bytes);
+    const int8_t *d_in = m->small_d_in;
+    int32_t *d_out = m->small_d_out;
+    if (m->small_zero_copy >= 2) CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(const_cast<int8_t **>(&d_in)), m->small_h_in, 0));
+    else CU_TRY(cudaMemcpyAsync(m->small_d_in, m->small_h_in, n * (size_t)m->img_bytes, cudaMemcpyHostToDevice, st));
+    if (m->small_zero_copy >= 1) CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_out), m->small_h_out, 0));
+    const size_t n_log = n * (size_t)m->n_classes;
+    uint32_t *d_lab = reinterpret_cast<uint32_t *>(d_out + n_log);
+    int rc = bnm_infer_batch_device(m, d_in, n, d_out, labels ? d_lab : nullptr, st);
+    if (rc) return rc;
+    if (m->small_zero_copy == 0) CU_TRY(cudaMemcpyAsync(m->small_h_out, m->small_d_out, (n_log + (labels ? n : 0)) * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    memcpy(logits, m->small_h_out, n_log * 4);
+    if (labels) memcpy(labels, m->small_h_out + n_log, n * 4);
+    return 0;
+}
+
 extern "C" int bnm_infer_batch(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels) {
     if (!m || (n && (!images || !logits))) return fail(BNM_E_ARG, "bnm_infer_batch: null argument");
     if (n == 0) return 0;
     CU_TRY(cudaSetDevice(m->device));
+    if (n <= kSmallBatch && n <= m->chunk_images) return infer_small(m, images, n, logits, labels);
     const size_t chunk = std::min(n, m->chunk_images);
     if (m->slot_n < chunk) {
         CU_TRY(cudaDeviceSynchronize());
@@ -488,6 +609,12 @@ struct DevBuf {
 
 static int require_device() {
     if (bnm_device_count() == 0) return fail(BNM_E_NODEV, "no CUDA device: this engine has no CPU fallback");
+    return 0;
+}
+static int require_device_index(int device) {
+    const int n = bnm_device_count();
+    if (n == 0) return fail(BNM_E_NODEV, "no CUDA device: this engine has no CPU fallback");
+    if (device < 0 || device >= n) return fail(BNM_E_ARG, "device %d out of range (have %d)", device, n);
     return 0;
 }
 

@@ -1,24 +1,36 @@
-// cnn_tcgen05.cu -- CNN front-end (BitNetMCU_MNIST_dll.c:64-80) with conv1 on the tensor cores.
+// cnn_tcgen05.cu -- CNN front-end (BitNetMCU_MNIST_dll.c:64-80) with conv1 on the tensor cores and its result consumed
+// straight out of TMEM by the depthwise tail.
 //
-// conv1 is the one convolution of the chain with a real reduction to share: 1 input channel -> C output channels,
-// out1[c][p] = sum_k w1[c][k] * patch[p][k].  im2col'd it is a GEMM with M = 196 positions x images, N = C, K = 9 (padded
-// to one K = 32 tcgen05 step): two MMA instructions per image instead of 588 dp4a per (image, channel) thread.  conv2 and
-// conv3 are depthwise (groups = C, models.py:111-118): as GEMMs they would be block diagonal (< 2 % utilisation), so they
-// stay on the CUDA cores exactly as in k_cnn_frontend16 and read conv1's output from shared memory.
+// conv1 (processconv33ReLU #1, inference.c:238-277 called at dll.c:71) is the one convolution of the chain with a reduction to
+// share: 1 input channel -> C output channels, out1[c][p] = sum_t w1[c][t] * patch[p][t].  conv2 / conv3 are depthwise
+// (groups = C, models.py:111-118): as GEMMs they are block diagonal (< 2 % tensor utilisation) and stay on the CUDA cores.
+// The GEMM is oriented so that the accumulator already has the layout the depthwise tail wants:
 //
-// Per group of ipb = 256 / C images (one CTA, 256 threads, persistent over groups):
-//   1. images -> smem, 4-byte sliding windows per image row (as k_cnn_frontend16)
-//   2. A operand: thread = output position, 9 patch bytes + 7 zeros -> one 16-byte store into the no-swizzle K-major
-//      core-matrix layout (8 rows x 16 B; the second K half stays zero); B operand = w1 in the same layout, built once
-//   3. one elected thread: tcgen05.mma kind::i8 M=128 N=round_up(C,16) K=32 per 128 positions, D int32 in TMEM
-//   4. epilogue: thread = position row, tcgen05.ld, ReLU >> 4 (inference.c:261-272) -> int16 planes [image][channel][196]
-//   5. thread = (image, channel): conv2 (dp2a) + pool + conv3 (IMAD) + pool + ReLUNorm over the C*4 features (dll.c:80)
-// All integer: bit-exact with the reference (27 CNN parity tests pass with BNM_CNN_TC=1, memcheck clean).
-// STATUS: experimental, off by default.  This first version runs the five phases one after the other in a single CTA per SM
-// (137 kB of shared memory for the int16 planes) and measures 0.093 G images/s (CNN-64) against 0.142 for k_cnn_frontend16,
-// whose two CTAs per SM keep 16 warps on the FMA-bound conv2.  What it establishes is the building block: conv1 as an
-// im2col'd tcgen05 GEMM, bit-exact.  To win it has to overlap the phases (two smaller CTAs per SM, or producer/consumer
-// warps with double-buffered planes) -- DESIGN.md section 7.
+//     D[M = (image, channel)][N = position]  =  A[(image, channel)][K = (image slot, tap)]  x  B[position][K]^T
+//
+//   * a TILE is 128 consecutive (image, channel) items = the 128 TMEM lanes = the 128 threads of a consumer warpgroup:
+//     thread r owns item r and reads ITS channel-image's 14 x 14 conv1 sums from its own TMEM lane with tcgen05.ld -- no
+//     shared-memory round trip, no transposition;
+//   * B is the im2col matrix of the images a tile touches: one 16-byte row (9 taps + padding) per (image, position),
+//     positions laid out with a row stride of 16 (N = 224 = 14 rows x 16, two accumulator halves of 112 columns), images side
+//     by side along K (16 bytes each), built by one producer warp per warpgroup with one 128-bit store per position;
+//   * A holds w1: row (image slot s, channel c) carries w1[c][0..8] in K-chunk s and zeros elsewhere, so one MMA computes
+//     conv1 of up to 128 / C images at once.  Tiles ignore image boundaries (item = image * C + channel), so every lane is
+//     used for any C that is a multiple of 16; a GROUP = 128 / gcd(C, 128) images is a whole number of tiles.
+//   * both operands use the no-swizzle K-major canonical layout (8 rows x 16 bytes core matrices) with K-chunks a whole
+//     plane apart: [K chunk][row][16 B], LBO = plane size, SBO = 128.
+//
+// Per (image, channel) thread, after tcgen05.ld of a conv1 row (14 int32 sums):
+//   ReLU >> 4 (inference.c:261-272)          : SHF.R.S32 + I2IP.U16.S32.SAT (packs two values, clamps negatives to 0)
+//   conv2, 12 x 12 outputs x 9 taps (dll.c:72): IDP.2A over int16 pairs, 5 per output: rows are processed in pairs (y, y+1) that
+//                                               share the vertical pair of their third column, so 6 PRMT per 24 outputs
+//   maxpool (dll.c:73)                        : taken on the raw sums BEFORE ReLU >> 4 (both are monotone): VIMNMX3.RELU + VIMNMX +
+//                                               SHF per pooled value instead of ReLU >> 4 on all 144 sums
+//   conv3 (dll.c:74), maxpool (dll.c:76)      : IMAD (int32 x int8), pooled the same way
+//   ReLUNorm over the C*4 features (dll.c:80)  : per-image maximum through shared memory once the group's tiles are done
+// The FMA pipe (IDP / IMAD issue, 2 cycles per warp instruction) bounds it: 720 IDP.2A + 144 IMAD per item, against
+// 588 IDP.4A + 720 IDP.2A + 196 IMAD for the CUDA-core kernel (generic_kernels.cu k_cnn_frontend16).
+// All integer: bit-exact with the reference.
 #include <cstdio>
 #include <cstdlib>
 
@@ -27,256 +39,372 @@
 
 namespace bnm {
 
-constexpr int kTcThreads = 256;
-constexpr uint32_t kPlaneStride = 198;   // int16 per (image, channel) plane: 196 values + 2 pad = 99 words -> conflict-free over channels
+constexpr uint32_t kCnnTcThreads = 320;          // 2 consumer warpgroups (8 warps) + 2 producer / MMA-issuer warps
+constexpr uint32_t kPlaneBytes = 224 * 16;       // im2col plane of one image: 14 rows x 16 positions x 16 bytes
+constexpr uint32_t kHalfCols = 112;              // accumulator half: conv1 rows 0..6 / 7..13, 16 columns each
 
-// kVer 1: 256 threads, all M tiles of a group in one MMA batch (up to 512 TMEM columns), one CTA per SM (validated, slow).
-// kVer 2: 128 threads, ipb = 128 / C images per group, one M tile at a time through a single 64-column accumulator, so three
-//         CTAs fit an SM (70 kB of shared memory, 64 TMEM columns each) and overlap each other's phases.  BNM_CNN_TC=2:
-//         bit-exact on hardware for both CNN fixtures (tools/cnn_tc_debug.py); throughput not measured yet.
-template <int kVer>
-__global__ void __launch_bounds__(kVer == 1 ? kTcThreads : 128, kVer == 1 ? 1 : 3)
-k_cnn_frontend16_tc(const int8_t *__restrict__ images, const int8_t *__restrict__ w1, const int8_t *__restrict__ w2,
-                    const int8_t *__restrict__ w3, uint32_t C, uint32_t n_pad, uint32_t ipb, uint32_t n_mtiles,
-                    int8_t *__restrict__ feats, uint32_t feat_stride, size_t n, int *err) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_mma;
-    __shared__ uint32_t tmem_base_s;
-    __shared__ int s_max[16];
-    const uint32_t t = threadIdx.x, lane = t & 31, n_thr = blockDim.x;
-    const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-    constexpr uint32_t kTmemCols = kVer == 1 ? 512 : 64;
+struct CnnTcParams {
+    const int8_t *images;
+    const int8_t *w1, *w2, *w3;
+    int8_t *feats;
+    uint32_t feat_stride;
+    size_t n;
+    int *err;
+    uint32_t C;
+    uint32_t G, T;                 // images / tiles per group
+    uint32_t a_plane_bytes;        // 128 rows x 16 B = 2048 (K-chunk stride of A)
+    uint32_t a_phase_bytes;        // one tile phase of A: n_chunks_max * 2048
+    uint32_t n_chunks_max;         // K-chunks (image slots) per tile, rounded up to even
+    // shared memory carve-up (byte offsets from the 128-aligned base)
+    uint32_t off_a, off_b, off_img, off_raw, off_wc, off_imax;
+    uint32_t b_buf_bytes;          // one im2col buffer: G + 1 planes
+    uint32_t raw_buf_bytes;        // T * 128 * 16
+    size_t n_groups;
+};
 
-    uint8_t *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    uint32_t *s_img = reinterpret_cast<uint32_t *>(base);             // [ipb][64] words = 16 rows x 16 bytes
-    uint32_t *s_win = s_img + ipb * 64;                               // [ipb][16][14] sliding 4-byte windows
-    uint8_t *s_a = reinterpret_cast<uint8_t *>(s_win + ipb * 224);    // [n_mtiles][128 rows x 32 B], canonical no-swizzle K-major
-    s_a += (128u - (smem_u32(s_a) & 127u)) & 127u;
-    uint8_t *s_b = s_a + n_mtiles * 4096;                             // [n_pad rows x 32 B], same layout
-    uint16_t *s_c1 = reinterpret_cast<uint16_t *>(s_b + n_pad * 32);  // [ipb][C][kPlaneStride] conv1 outputs (ReLU >> 4 < 2^15)
+__device__ __forceinline__ uint32_t pack_relu_u16(int hi, int lo) {
+    uint32_t d;   // (clamp(hi, 0, 65535) << 16) | clamp(lo, 0, 65535): the ReLU comes with the conversion
+    asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
 
-    // ---- one-time setup
-    if (t == 0) { mbar_init(&bar_mma, 1); fence_mbar_init(); }
-    if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_s);
-    for (uint32_t i = t; i < n_mtiles * 256; i += n_thr) reinterpret_cast<uint4 *>(s_a)[i] = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = t; i < n_pad * 32; i += n_thr) {
-        const uint32_t nn = i >> 5, k = i & 31;
-        const int8_t v = (nn < C && k < 9) ? w1[nn * 9 + k] : (int8_t)0;
-        s_b[(nn >> 3) * 256 + (k >> 4) * 128 + (nn & 7) * 16 + (k & 15)] = (uint8_t)v;
+// per-channel weights of the depthwise tail, 16 words
+struct CnnTailW {
+    int w01[3];        // conv2 kernel row r: (w[r][0], w[r][1]) as int8 pair in the low two bytes
+    int wva, wvb;      // third column, vertical pairs: (w[1][2], w[2][2]) for the upper row of a pair, (w[0][2], w[1][2]) for the lower
+    int wsa, wsb;      // third column, single taps: (w[0][2], 0) and (w[2][2], 0)
+    int k3[9];         // conv3
+};
+
+// One tile of one consumer thread: conv1 sums from TMEM -> 4 raw features (before ReLUNorm) of this (image, channel).
+// tm = TMEM address of this thread's lane quarter at the warpgroup's first accumulator column.
+__device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, uint32_t bar_full1, uint32_t bar_free0,
+                                              uint32_t bar_free1, uint32_t parity, const CnnTailW &W, int (&f)[4], int *err) {
+    uint32_t E[14][7], O[14][7];   // conv1 rows as int16 pairs: E[y][j] = (v[2j], v[2j+1]), O[y][j] = (v[2j+1], v[2j+2]); 4 rows live
+    int pl[6][6];                  // pooled conv2 rows (3 live)
+    int c3e[4];
+    uint32_t cur[16], nxt[16];
+    mbar_wait_a(bar_full0, parity, err, 11);
+    tc_fence_after();
+    tmem_ld_x16(tm, cur);
+    tmem_ld_wait_x16(cur);
+#pragma unroll
+    for (int y = 0; y < 14; y++) {
+        if (y + 1 < 14) {
+            if (y + 1 == 7) {
+                mbar_wait_a(bar_full1, parity, err, 12);
+                tc_fence_after();
+            }
+            tmem_ld_x16(tm + (y + 1) * 16, nxt);   // prefetch the next conv1 row while this one is processed
+        }
+        {   // ReLU >> 4 of conv1 (inference.c:261-272) and int16 pairing
+            int t[14];
+#pragma unroll
+            for (int x = 0; x < 14; x++) t[x] = (int)cur[x] >> 4;   // floor(s / 16); negatives stay negative and clamp to 0 below
+#pragma unroll
+            for (int j = 0; j < 7; j++) E[y][j] = pack_relu_u16(t[2 * j + 1], t[2 * j]);
+#pragma unroll
+            for (int j = 0; j < 6; j++) O[y][j] = __byte_perm(E[y][j], E[y][j + 1], 0x5432);
+            O[y][6] = E[y][6] >> 16;
+        }
+        if (y >= 3 && (y & 1)) {
+            // conv2 output rows (y-3, y-2) from conv1 rows R0..R3 = y-3..y, pooled into row p
+            const int p = (y - 3) >> 1, R0 = y - 3, R1 = y - 2, R2 = y - 1, R3 = y;
+#define BNM_P(r, x) (((x) & 1) ? O[r][(x) >> 1] : E[r][(x) >> 1])
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                int a[2], b[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int x = 2 * j + e;
+                    const int v = (int)__byte_perm(BNM_P(R1, x + 2), BNM_P(R2, x + 2), 0x5410);   // (R1[x+2], R2[x+2])
+                    int s = __dp2a_lo((int)BNM_P(R0, x), W.w01[0], 0);
+                    s = __dp2a_lo((int)BNM_P(R1, x), W.w01[1], s);
+                    s = __dp2a_lo((int)BNM_P(R2, x), W.w01[2], s);
+                    s = __dp2a_lo(v, W.wva, s);
+                    a[e] = __dp2a_lo((int)BNM_P(R0, x + 2), W.wsa, s);
+                    int u = __dp2a_lo((int)BNM_P(R1, x), W.w01[0], 0);
+                    u = __dp2a_lo((int)BNM_P(R2, x), W.w01[1], u);
+                    u = __dp2a_lo((int)BNM_P(R3, x), W.w01[2], u);
+                    u = __dp2a_lo(v, W.wvb, u);
+                    b[e] = __dp2a_lo((int)BNM_P(R3, x + 2), W.wsb, u);
+                }
+                pl[p][j] = max(__vimax3_s32_relu(a[0], a[1], b[0]), b[1]) >> 4;   // maxpool, then ReLU >> 4 (monotone: same result)
+            }
+#undef BNM_P
+            if (p >= 2) {
+                const int q = p - 2;   // conv3 output row
+                int u[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    int s = 0;
+#pragma unroll
+                    for (int dr = 0; dr < 3; dr++)
+#pragma unroll
+                        for (int dc = 0; dc < 3; dc++) s += W.k3[3 * dr + dc] * pl[q + dr][x + dc];
+                    u[x] = s;
+                }
+                if ((q & 1) == 0) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) c3e[x] = u[x];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        f[(q >> 1) * 2 + j] = max(__vimax3_s32_relu(c3e[2 * j], c3e[2 * j + 1], u[2 * j]), u[2 * j + 1]) >> 4;
+                }
+            }
+        }
+        if (y + 1 < 14) {
+            tmem_ld_wait_x16(nxt);
+            if (y + 1 == 6 || y + 1 == 13) {   // the last row of an accumulator half is in registers: the half may be overwritten
+                tc_fence_before();
+                mbar_arrive_a(y + 1 == 6 ? bar_free0 : bar_free1);
+            }
+#pragma unroll
+            for (int x = 0; x < 16; x++) cur[x] = nxt[x];
+        }
     }
+}
+
+__global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __grid_constant__ CnnTcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[2][2], bar_free[2][2];   // [warpgroup][accumulator half]
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t t = threadIdx.x, lane = t & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+    uint8_t *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    const uint32_t C = P.C, G = P.G, T = P.T;
+
+    // ---- one-time setup: barriers, TMEM, the A operand (w1 per tile phase), per-channel tail weights
+    if (t == 0) {
+#pragma unroll
+        for (int g = 0; g < 2; g++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) { mbar_init(&bar_full[g][h], 1); mbar_init(&bar_free[g][h], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc<512>(&tmem_base_s);
+    {
+        uint4 *a4 = reinterpret_cast<uint4 *>(base + P.off_a);
+        const uint32_t total = T * P.n_chunks_max * 128;   // 16-byte rows
+        for (uint32_t i = t; i < total; i += kCnnTcThreads) {
+            const uint32_t phase = i / (P.n_chunks_max * 128), rem = i % (P.n_chunks_max * 128), chunk = rem >> 7, r = rem & 127;
+            const uint32_t item = phase * 128 + r, il = item / C, ch = item % C, i0 = (phase * 128) / C;
+            uint32_t q[4] = {0, 0, 0, 0};
+            if (il - i0 == chunk) {
+                const int8_t *w = P.w1 + ch * 9;
+#pragma unroll
+                for (int k = 0; k < 9; k++) q[k >> 2] |= (uint32_t)(uint8_t)w[k] << (8 * (k & 3));
+            }
+            a4[i] = make_uint4(q[0], q[1], q[2], q[3]);   // [phase][chunk][row][16 B]
+        }
+        int *wc = reinterpret_cast<int *>(base + P.off_wc);
+        for (uint32_t ch = t; ch < C; ch += kCnnTcThreads) {
+            const int8_t *b = P.w2 + ch * 9, *c = P.w3 + ch * 9;
+            auto pair = [](int8_t lo, int8_t hi) { return (int)((uint32_t)(uint8_t)lo | ((uint32_t)(uint8_t)hi << 8)); };
+            int *o = wc + ch * 16;
+            o[0] = pair(b[0], b[1]); o[1] = pair(b[3], b[4]); o[2] = pair(b[6], b[7]);
+            o[3] = pair(b[5], b[8]); o[4] = pair(b[2], b[5]);
+            o[5] = pair(b[2], 0); o[6] = pair(b[8], 0);
+#pragma unroll
+            for (int k = 0; k < 9; k++) o[7 + k] = c[k];
+        }
+        int *imax = reinterpret_cast<int *>(base + P.off_imax);
+        for (uint32_t i = t; i < 2 * 3 * 8; i += kCnnTcThreads) imax[i] = 0;
+    }
+    fence_proxy_async_smem();   // the tensor core (async proxy) reads A
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const uint64_t b_desc = make_smem_desc(smem_u32(s_b), 128, 256, UMMA_LAYOUT_NONE);
-    const uint32_t idesc = make_idesc_i8(128, n_pad);
-    uint32_t mma_phase = 0;
 
-    const bool active = t < ipb * C;
-    const uint32_t il = active ? t / C : 0, ch = active ? t % C : 0;
-    int w2p[3], k3[9], w2v, w2s;   // conv2: (w0, w1) per kernel row + the third column; conv3: scalars
-    {
-        const int8_t *b = w2 + ch * 9, *c = w3 + ch * 9;
+    if (warp >= 8) {
+        // ======================= producer + MMA issuer of warpgroup g =======================
+        const uint32_t g = warp - 8;
+        const bool leader = elect_one();
+        uint32_t *s_img = reinterpret_cast<uint32_t *>(base + P.off_img + g * (8 * 256 + 64));
+        const uint32_t n_ld = (G * 16 + 31) / 32;   // 16-byte loads per lane and group (<= 4)
+        const uint32_t idesc = make_idesc_i8(128, kHalfCols);
+        const uint32_t a_base = smem_u32(base + P.off_a);
+        uint32_t free_phase = 0;   // one bit per half; a fresh barrier passes a wait on parity 1
+        uint4 img_regs[4];
+        auto load_group = [&](size_t grp) {   // global -> registers (latency hidden behind the previous group's work)
 #pragma unroll
-        for (int r = 0; r < 3; r++) w2p[r] = (int)((uint32_t)(uint8_t)b[3 * r] | ((uint32_t)(uint8_t)b[3 * r + 1] << 8));
-#pragma unroll
-        for (int i = 0; i < 9; i++) k3[i] = c[i];
-        w2v = (int)((uint32_t)(uint8_t)b[2] | ((uint32_t)(uint8_t)b[5] << 8));
-        w2s = (int)(uint32_t)(uint8_t)b[8];
-    }
-
-    const uint32_t n_pos = ipb * 196;
-    const size_t n_groups = (n + ipb - 1) / ipb;
-    for (size_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const size_t img_base = g * ipb;
-        // ---- 1. images and their sliding windows
-        for (uint32_t idx = t; idx < ipb * 64; idx += n_thr) {
-            const size_t img = img_base + idx / 64;
-            s_img[idx] = img < n ? reinterpret_cast<const uint32_t *>(images)[img * 64 + (idx & 63)] : 0u;
-        }
-        if (t < ipb) s_max[t] = 0;
-        __syncthreads();
-        for (uint32_t idx = t; idx < ipb * 224; idx += n_thr) {
-            const uint32_t im = idx / 224, r = (idx % 224) / 14, x = idx % 14;
-            const uint32_t lo = s_img[im * 64 + r * 4 + (x >> 2)];
-            const uint32_t hi = (x >> 2) < 3 ? s_img[im * 64 + r * 4 + (x >> 2) + 1] : 0u;
-            s_win[idx] = __funnelshift_r(lo, hi, 8 * (x & 3));
-        }
-        __syncthreads();
-        // ---- 2. im2col rows: (a0 a1 a2 b0 | b1 b2 c0 c1 | c2 0 0 0 | 0 0 0 0) = taps in the order of w1[c][0..8]
-        for (uint32_t R = t; R < n_pos; R += n_thr) {
-            const uint32_t im = R / 196, pos = R % 196, y = pos / 14, x = pos % 14;
-            const uint32_t *wrow = s_win + im * 224 + y * 14 + x;
-            const uint32_t wa = wrow[0], wb = wrow[14], wc = wrow[28];
-            uint4 q;
-            q.x = __byte_perm(wa, wb, 0x4210);
-            q.y = __byte_perm(wb, wc, 0x5421);
-            q.z = (wc >> 16) & 0xffu;
-            q.w = 0;
-            const uint32_t tile = R >> 7, r = R & 127;
-            *reinterpret_cast<uint4 *>(s_a + tile * 4096 + (r >> 3) * 256 + (r & 7) * 16) = q;
-        }
-        fence_proxy_async_smem();   // the tensor core (async proxy) reads what these generic stores wrote
-        __syncthreads();
-        // ---- 3 + 4. conv1 for all channels of all positions (one MMA per 128 positions), then ReLU >> 4 -> int16 planes
-        //             [image][channel][position]; epilogue thread = position row (TMEM lane)
-        auto drain_tile = [&](uint32_t tile, uint32_t d_col) {
-            const uint32_t R = tile * 128 + (warp & 3) * 32 + lane;
-            const bool valid = R < n_pos;
-            const uint32_t im = valid ? R / 196 : 0, pos = valid ? R % 196 : 0;
-            uint16_t *dst = s_c1 + (size_t)im * C * kPlaneStride + pos;
-            for (uint32_t c0 = 0; c0 < n_pad; c0 += 16) {
-                uint32_t x[16];
-                tmem_ld_x16(tmem_base + (((warp & 3) * 32) << 16) + d_col + c0, x);
-                tmem_ld_wait();
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (c0 + j < C) dst[(c0 + j) * kPlaneStride] = (uint16_t)(max((int)x[j], 0) >> 4);
-                }
+            for (uint32_t k = 0; k < 4; k++) {
+                img_regs[k] = make_uint4(0, 0, 0, 0);
+                const uint32_t idx = k * 32 + lane;   // uint4 index inside the group: image = idx / 16
+                if (k < n_ld && idx < G * 16 && grp * G + idx / 16 < P.n)
+                    img_regs[k] = reinterpret_cast<const uint4 *>(P.images)[grp * G * 16 + idx];
             }
         };
-        if (kVer == 1) {
-            if (warp == 0) {
+        auto build_group = [&](uint32_t buf) {   // registers -> s_img -> im2col planes of buffer buf
+            __syncwarp();
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t idx = k * 32 + lane;
+                if (k < n_ld && idx < G * 16) reinterpret_cast<uint4 *>(s_img)[idx] = img_regs[k];
+            }
+            __syncwarp();
+            uint8_t *bbuf = base + P.off_b + (g * 2 + buf) * P.b_buf_bytes;
+#pragma unroll 1
+            for (uint32_t idx = lane; idx < G * 196; idx += 32) {
+                const uint32_t im = idx / 196, pos = idx - im * 196, y = pos / 14, x = pos - y * 14;
+                const uint32_t *row = s_img + im * 64 + y * 4 + (x >> 2);
+                const uint32_t sh = 8 * (x & 3);
+                const uint32_t wa = __funnelshift_r(row[0], row[1], sh), wb = __funnelshift_r(row[4], row[5], sh),
+                               wc = __funnelshift_r(row[8], row[9], sh);
+                // taps in the order of w1[c][0..8]: (a0 a1 a2 b0 | b1 b2 c0 c1 | c2 . . . | . . . .); bytes 9..15 meet zeros in A
+                uint4 q;
+                q.x = __byte_perm(wa, wb, 0x4210);
+                q.y = __byte_perm(wb, wc, 0x5421);
+                q.z = wc >> 16;
+                q.w = 0;
+                *reinterpret_cast<uint4 *>(bbuf + im * kPlaneBytes + (y * 16 + x) * 16) = q;
+            }
+            fence_proxy_async_smem();   // the MMAs (async proxy) read what these generic-proxy stores wrote
+            __syncwarp();
+        };
+        auto issue_tile = [&](uint32_t buf, uint32_t tau) {
+            const uint32_t i0 = (tau * 128) / C, i1 = (tau * 128 + 127) / C;
+            const uint32_t n_k = (i1 - i0 + 2) / 2;   // K-steps of 32 bytes = two image slots
+            const uint32_t b_base = smem_u32(base + P.off_b + (g * 2 + buf) * P.b_buf_bytes) + i0 * kPlaneBytes;
+            for (uint32_t h = 0; h < 2; h++) {
+                mbar_wait(&bar_free[g][h], ((free_phase >> h) & 1) ^ 1, P.err, 13);
+                free_phase ^= 1u << h;
                 tc_fence_after();
-                if (elect_one()) {
-                    for (uint32_t tile = 0; tile < n_mtiles; tile++)
-                        umma_i8_ss(tmem_base + tile * n_pad, make_smem_desc(smem_u32(s_a) + tile * 4096, 128, 256, UMMA_LAYOUT_NONE), b_desc, idesc, 0);
-                    umma_commit(&bar_mma);
+                const uint32_t d_tmem = tmem_base + g * 224 + h * kHalfCols;
+                for (uint32_t s = 0; s < n_k; s++) {
+                    const uint64_t ad = make_smem_desc(a_base + tau * P.a_phase_bytes + s * 2 * P.a_plane_bytes, P.a_plane_bytes, 128, UMMA_LAYOUT_NONE);
+                    const uint64_t bd = make_smem_desc(b_base + s * 2 * kPlaneBytes + h * kHalfCols * 16, kPlaneBytes, 128, UMMA_LAYOUT_NONE);
+                    if (leader) umma_i8_ss(d_tmem, ad, bd, idesc, s != 0);
                 }
+                if (leader) umma_commit(&bar_full[g][h]);
                 __syncwarp();
             }
-            mbar_wait(&bar_mma, mma_phase, err, 7);
-            mma_phase ^= 1;
-            tc_fence_after();
-            // warps w and w+4 share a lane quarter and take alternate tiles
-            for (uint32_t tile = warp >> 2; tile < n_mtiles; tile += 2) drain_tile(tile, tile * n_pad);
-            tc_fence_before();
-            __syncthreads();
-        } else {
-            for (uint32_t tile = 0; tile < n_mtiles; tile++) {   // one accumulator, tile by tile; the other CTAs of the SM fill the gaps
-                if (warp == 0) {
-                    tc_fence_after();
-                    if (elect_one()) {
-                        umma_i8_ss(tmem_base, make_smem_desc(smem_u32(s_a) + tile * 4096, 128, 256, UMMA_LAYOUT_NONE), b_desc, idesc, 0);
-                        umma_commit(&bar_mma);
-                    }
-                    __syncwarp();
-                }
-                mbar_wait(&bar_mma, mma_phase, err, 7);
-                mma_phase ^= 1;
-                tc_fence_after();
-                drain_tile(tile, 0);
-                tc_fence_before();
-                __syncthreads();   // every warp has read D before the next MMA overwrites it
+        };
+        // groups of this warpgroup: j = (k * gridDim + blockIdx) * 2 + g
+        const size_t stride = (size_t)gridDim.x * 2;
+        size_t j = (size_t)blockIdx.x * 2 + g;
+        uint32_t buf = 0;
+        if (j < P.n_groups) {
+            load_group(j);
+            build_group(0);
+            if (j + stride < P.n_groups) load_group(j + stride);
+        }
+        for (; j < P.n_groups; j += stride, buf ^= 1) {
+            issue_tile(buf, 0);
+            // Every MMA of the group before this one has completed (its last accumulator halves were drained before the waits
+            // above passed): the other im2col buffer is free for the next group.
+            if (j + stride < P.n_groups) {
+                build_group(buf ^ 1);
+                if (j + 2 * stride < P.n_groups) load_group(j + 2 * stride);
             }
+            for (uint32_t tau = 1; tau < T; tau++) issue_tile(buf, tau);
         }
-        // ---- 5. depthwise tail on the CUDA cores: thread = (image, channel)
-        int f[4] = {0, 0, 0, 0};
-        if (active) {
-            const uint32_t *pw = reinterpret_cast<const uint32_t *>(s_c1 + (size_t)(il * C + ch) * kPlaneStride);   // 7 words per row
-            uint32_t c1[3][14];   // rolling conv1 rows as int16 pairs: c1[.][x] = (v[x], v[x+1]), c1[.][13] = (v[13], 0)
-            int c2e[12], pl[3][6], c3e[4];
-#pragma unroll
-            for (int y = 0; y < 14; y++) {
-                uint32_t W[7];
-#pragma unroll
-                for (int j = 0; j < 7; j++) W[j] = pw[y * 7 + j];
-#pragma unroll
-                for (int x = 0; x < 14; x++)
-                    c1[y % 3][x] = (x & 1) ? __byte_perm(W[x >> 1], x < 13 ? W[(x >> 1) + 1] : 0u, 0x5432) : W[x >> 1];
-                if (y >= 2) {
-                    const int r = y - 2;  // conv2 output row
-                    int v[12];
-#pragma unroll
-                    for (int x = 0; x < 12; x++) {
-                        int s = __dp2a_lo((int)c1[r % 3][x], w2p[0], 0);
-                        s = __dp2a_lo((int)c1[(r + 1) % 3][x], w2p[1], s);
-                        s = __dp2a_lo((int)c1[(r + 2) % 3][x], w2p[2], s);
-                        s = __dp2a_lo((int)__byte_perm(c1[r % 3][x + 2], c1[(r + 1) % 3][x + 2], 0x5410), w2v, s);
-                        s = __dp2a_lo((int)c1[(r + 2) % 3][x + 2], w2s, s);
-                        v[x] = max(s, 0) >> 4;
-                    }
-                    if ((r & 1) == 0) {
-#pragma unroll
-                        for (int x = 0; x < 12; x++) c2e[x] = v[x];
-                    } else {
-                        const int p = r >> 1;  // pooled row 0..5
-#pragma unroll
-                        for (int j = 0; j < 6; j++) pl[p % 3][j] = max(max(c2e[2 * j], c2e[2 * j + 1]), max(v[2 * j], v[2 * j + 1]));
-                        if (p >= 2) {
-                            const int q = p - 2;  // conv3 output row 0..3
-                            int u[4];
-#pragma unroll
-                            for (int x = 0; x < 4; x++) {
-                                int s = 0;
-#pragma unroll
-                                for (int dr = 0; dr < 3; dr++)
-#pragma unroll
-                                    for (int dc = 0; dc < 3; dc++) s += k3[3 * dr + dc] * pl[(q + dr) % 3][x + dc];
-                                u[x] = max(s, 0) >> 4;
-                            }
-                            if ((q & 1) == 0) {
-#pragma unroll
-                                for (int x = 0; x < 4; x++) c3e[x] = u[x];
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 2; j++)
-                                    f[(q >> 1) * 2 + j] = max(max(c3e[2 * j], c3e[2 * j + 1]), max(u[2 * j], u[2 * j + 1]));
-                            }
-                        }
-                    }
+    } else {
+        // ======================= consumer warpgroup g: thread r = TMEM lane r =======================
+        const uint32_t g = warp >> 2, r = t & 127;
+        const uint32_t tm = tmem_base + (((warp & 3) * 32) << 16) + g * 224;
+        const uint32_t bf0 = smem_u32(&bar_full[g][0]), bf1 = smem_u32(&bar_full[g][1]);
+        const uint32_t be0 = smem_u32(&bar_free[g][0]), be1 = smem_u32(&bar_free[g][1]);
+        const int *wc = reinterpret_cast<const int *>(base + P.off_wc);
+        int *imax = reinterpret_cast<int *>(base + P.off_imax) + g * 24;   // [3][8]
+        uint32_t parity = 0, gcount = 0;
+        const size_t stride = (size_t)gridDim.x * 2;
+        for (size_t j = (size_t)blockIdx.x * 2 + g; j < P.n_groups; j += stride, gcount++) {
+            int4 *raw = reinterpret_cast<int4 *>(base + P.off_raw + (g * 2 + (gcount & 1)) * P.raw_buf_bytes);
+            int *imx = imax + (gcount % 3) * 8;
+            for (uint32_t tau = 0; tau < T; tau++, parity ^= 1) {
+                const uint32_t item = tau * 128 + r, il = item / C, ch = item - il * C;
+                CnnTailW W;
+                {
+                    const int4 *w4 = reinterpret_cast<const int4 *>(wc + ch * 16);
+                    const int4 q0 = w4[0], q1 = w4[1], q2 = w4[2], q3 = w4[3];
+                    W.w01[0] = q0.x; W.w01[1] = q0.y; W.w01[2] = q0.z; W.wva = q0.w;
+                    W.wvb = q1.x; W.wsa = q1.y; W.wsb = q1.z; W.k3[0] = q1.w;
+                    W.k3[1] = q2.x; W.k3[2] = q2.y; W.k3[3] = q2.z; W.k3[4] = q2.w;
+                    W.k3[5] = q3.x; W.k3[6] = q3.y; W.k3[7] = q3.z; W.k3[8] = q3.w;
                 }
+                int f[4] = {0, 0, 0, 0};
+                cnn_tile_tail(tm, bf0, bf1, be0, be1, parity, W, f, P.err);
+                raw[item] = make_int4(f[0], f[1], f[2], f[3]);
+                atomicMax(&imx[il], max(max(f[0], f[1]), max(f[2], f[3])));
             }
-            atomicMax(&s_max[il], max(max(f[0], f[1]), max(f[2], f[3])));
+            named_bar_sync(1 + g, 128);   // the group's raw features and per-image maxima are complete
+            // ReLUNorm over the C*4 features of each image (dll.c:80): all features are >= 0 here
+            for (uint32_t it = 0; it < T; it++) {
+                const uint32_t item = it * 128 + r, il = item / C, ch = item - il * C;
+                const size_t img = j * G + il;
+                const int m = imx[il];
+                const uint32_t shift = 32u - (uint32_t)__clz(m >> 7);   // bit length of max >> 7 (inference.c:41-47)
+                const int rounding = (int)((1u << shift) >> 1);
+                const int4 v = raw[item];
+                const uint32_t packed = (uint32_t)min(127, (v.x + rounding) >> shift) | ((uint32_t)min(127, (v.y + rounding) >> shift) << 8) |
+                                        ((uint32_t)min(127, (v.z + rounding) >> shift) << 16) | ((uint32_t)min(127, (v.w + rounding) >> shift) << 24);
+                if (img < P.n) *reinterpret_cast<uint32_t *>(P.feats + img * P.feat_stride + ch * 4) = packed;
+            }
+            // the maxima buffer of the group after next (last read two groups ago, behind a barrier) is cleared here
+            if (r < 8) imax[((gcount + 2) % 3) * 8 + r] = 0;
         }
-        __syncthreads();
-        if (active && img_base + il < n) {
-            // ReLUNorm over the C*4 features of this image (dll.c:80); all features are >= 0 here
-            const uint32_t shift = 32u - (uint32_t)__clz(s_max[il] >> 7);   // bit length of max >> 7 (inference.c:41-47)
-            const int rounding = (int)((1u << shift) >> 1);
-            uint32_t packed = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) packed |= (uint32_t)min(127, (f[j] + rounding) >> shift) << (8 * j);
-            *reinterpret_cast<uint32_t *>(feats + (img_base + il) * feat_stride + ch * 4) = packed;
-        }
-        __syncthreads();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+static uint32_t gcd_u32(uint32_t a, uint32_t b) { return b ? gcd_u32(b, a % b) : a; }
+
+// geometry + shared-memory carve-up for a channel count; returns the dynamic shared memory needed, 0 when the shape is not covered
+static size_t cnn_tc_plan(uint32_t channels, uint32_t xy, CnnTcParams &p) {
+    if (xy != 16 || channels < 16 || channels > 128 || channels % 16) return 0;
+    p.C = channels;
+    p.G = 128 / gcd_u32(channels, 128);
+    p.T = p.G * channels / 128;
+    uint32_t max_imgs = 1;
+    for (uint32_t tau = 0; tau < p.T; tau++) max_imgs = std::max(max_imgs, (tau * 128 + 127) / channels - (tau * 128) / channels + 1);
+    p.n_chunks_max = (max_imgs + 1) / 2 * 2;
+    p.a_plane_bytes = 128 * 16;
+    p.a_phase_bytes = p.n_chunks_max * p.a_plane_bytes;
+    p.b_buf_bytes = (p.G + 1) * kPlaneBytes;   // + one spare plane: an odd image count reads one zero-weighted chunk past the last image
+    p.raw_buf_bytes = p.T * 128 * 16;
+    uint32_t off = 0;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 127) / 128 * 128; return o; };
+    p.off_a = take(p.T * p.a_phase_bytes);
+    p.off_b = take(4 * p.b_buf_bytes);
+    p.off_img = take(2 * (8 * 256 + 64));
+    p.off_raw = take(4 * p.raw_buf_bytes);
+    p.off_wc = take(channels * 64);
+    p.off_imax = take(2 * 3 * 8 * 4);
+    const size_t smem = (size_t)off + 128;
+    return smem <= 226 * 1024 ? smem : 0;
+}
+
+bool cnn_frontend_tc_supported(uint32_t channels, uint32_t xy) {
+    CnnTcParams p{};
+    return cnn_tc_plan(channels, xy, p) != 0;
 }
 
 // returns false when the shape is not covered (the caller then uses k_cnn_frontend16)
 bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
-                            uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err, int version,
+                            uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err,
                             cudaStream_t st) {
-    if (xy != 16 || channels < 16 || channels > 64) return false;
-    const uint32_t threads = version == 2 ? 128 : kTcThreads;
-    const uint32_t ipb = threads / channels;
-    if (ipb == 0 || ipb > 16) return false;
-    const uint32_t n_pad = (channels + 15) / 16 * 16;
-    const uint32_t n_mtiles = (ipb * 196 + 127) / 128;
-    if (version != 2 && n_mtiles * n_pad > 512) return false;
-    const size_t smem = 256 + (size_t)ipb * (64 + 224) * 4 + (size_t)n_mtiles * 4096 + (size_t)n_pad * 32 +
-                        (size_t)ipb * channels * kPlaneStride * 2 + 64;
-    if (smem > 226 * 1024) return false;
-    static size_t attr_bytes[2] = {0, 0};   // opt-in dynamic shared memory granted so far (static + dynamic must stay <= 227 kB)
-    const int vi = version == 2 ? 1 : 0;
-    if (smem > attr_bytes[vi]) {
-        const cudaError_t e = vi ? cudaFuncSetAttribute(k_cnn_frontend16_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                 : cudaFuncSetAttribute(k_cnn_frontend16_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
+    CnnTcParams p{};
+    size_t smem = cnn_tc_plan(channels, xy, p);
+    if (!smem) return false;
+    smem = std::max<size_t>(smem, 116 * 1024);   // one CTA per SM (each allocates all 512 TMEM columns): more than half of the shared memory
+    p.images = images; p.w1 = w1; p.w2 = w2; p.w3 = w3; p.feats = features; p.feat_stride = feat_stride; p.n = n; p.err = d_err;
+    p.n_groups = (n + p.G - 1) / p.G;
+    static size_t granted = 0;
+    if (smem > granted) {
+        if (cudaFuncSetAttribute(k_cnn_frontend16_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();   // not sticky: leave no stale error behind for the caller's launch check
             return false;
         }
-        attr_bytes[vi] = smem;
+        granted = smem;
     }
-    const size_t n_groups = (n + ipb - 1) / ipb;
-    const size_t max_ctas = (size_t)sm_count * (vi ? 3 : 1);
-    const unsigned grid = (unsigned)(n_groups < max_ctas ? n_groups : max_ctas);
-    if (vi) k_cnn_frontend16_tc<2><<<grid, threads, smem, st>>>(images, w1, w2, w3, channels, n_pad, ipb, n_mtiles, features, feat_stride, n, d_err);
-    else k_cnn_frontend16_tc<1><<<grid, threads, smem, st>>>(images, w1, w2, w3, channels, n_pad, ipb, n_mtiles, features, feat_stride, n, d_err);
+    const size_t want = (p.n_groups + 1) / 2;
+    const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sm_count);
+    k_cnn_frontend16_tc<<<grid, kCnnTcThreads, smem, st>>>(p);
     return true;
 }
 

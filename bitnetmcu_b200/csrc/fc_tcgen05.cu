@@ -54,6 +54,12 @@ struct ChainParams {
     uint32_t stagger_cycles;          // tuning knob (BNM_STAGGER_NS): warpgroup g starts no earlier than g * this after kernel entry
     uint32_t wait_prior_grid;         // programmatic dependent launch: read inputs only after the previous kernel has completed
     uint32_t early_trigger;           // let the next launch's CTAs take over SMs as this launch's CTAs leave (full grids only)
+    // result exchange fused into the epilogue: besides logits / labels, row i of this launch is also stored at row
+    // row0 + i of every destination buffer -- peer GPUs' memory mapped through CUDA IPC / P2P, written over NVLink
+    uint32_t n_lab_dst, n_log_dst;
+    uint32_t *lab_dst[kMaxGatherDst];
+    int32_t *log_dst[kMaxGatherDst];
+    size_t row0;
 };
 
 struct FcChainPlan {
@@ -246,7 +252,7 @@ __device__ __forceinline__ void issue_layer_ts(const ChainParams &P, int l, uint
             if (leader) umma_i8_ts(d_tmem, a_tmem + k * 8, b0 + bo, idesc, bo != 0);
 }
 
-template <int kSlots, bool kTrace>
+template <int kSlots, bool kTrace, bool kGather>
 __global__ void __launch_bounds__(kMaxWG * 160, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -430,15 +436,20 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                                 key = __vimax3_s32(key, (int)x[j] * 16 + P.kadd[j], (int)x[j + 1] * 16 + P.kadd[j + 1]);
                             pos = 15 - (key & 15);
                             if (full_tile || img < P.n) {
-                                if ((ncls & 1) == 0) {   // rows are 8-byte aligned: 64-bit stores straight to HBM (write-combined in L2)
+                                auto store_row = [&](int32_t *d) {
+                                    if ((ncls & 1) == 0) {   // rows are 8-byte aligned: 64-bit stores straight to HBM (write-combined in L2)
 #pragma unroll
-                                    for (int j = 0; j < 16; j += 2)
-                                        if ((uint32_t)j < ncls) *reinterpret_cast<int2 *>(dst + j) = make_int2((int)x[j], (int)x[j + 1]);
-                                } else {
+                                        for (int j = 0; j < 16; j += 2)
+                                            if ((uint32_t)j < ncls) *reinterpret_cast<int2 *>(d + j) = make_int2((int)x[j], (int)x[j + 1]);
+                                    } else {
 #pragma unroll
-                                    for (int j = 0; j < 16; j++)
-                                        if ((uint32_t)j < ncls) dst[j] = (int)x[j];
-                                }
+                                        for (int j = 0; j < 16; j++)
+                                            if ((uint32_t)j < ncls) d[j] = (int)x[j];
+                                    }
+                                };
+                                store_row(dst);
+                                if (kGather)
+                                    for (uint32_t d = 0; d < P.n_log_dst; d++) store_row(P.log_dst[d] + (P.row0 + img) * ncls);   // peers, over NVLink
                             }
                         } else {
                             int best = -INT32_MAX;
@@ -460,12 +471,21 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 #pragma unroll
                                     for (int j = 0; j < 16; j++)
                                         if (c + j < ncls) dst[c + j] = (int)x[j];
+                                    for (uint32_t d = 0; kGather && d < P.n_log_dst; d++) {
+                                        int32_t *pd = P.log_dst[d] + (P.row0 + img) * ncls;
+#pragma unroll
+                                        for (int j = 0; j < 16; j++)
+                                            if (c + j < ncls) pd[c + j] = (int)x[j];
+                                    }
                                 }
                             }
                             tc_fence_before();
                             mbar_arrive_a(bar_ready0 + q * 8);
                         }
-                        if (P.labels && (full_tile || img < P.n)) P.labels[img] = pos;
+                        if (full_tile || img < P.n) {
+                            if (P.labels) P.labels[img] = pos;
+                            for (uint32_t d = 0; kGather && d < P.n_lab_dst; d++) P.lab_dst[d][P.row0 + img] = pos;
+                        }
                     }
                     BNM_TRACE_POINT();   // step end
                 }
@@ -579,10 +599,12 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     if (cudaDeviceSynchronize() != cudaSuccess) { fc_chain_plan_destroy(plan); return fail("weight image kernel failed"); }
     p.w_image = plan->d_w_image;
     p.err = plan->d_err;
-    if (cudaFuncSetAttribute(fc_chain_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(fc_chain_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
         return fail("cannot opt in to the required dynamic shared memory");
     }
@@ -625,20 +647,31 @@ static const CUtensorMap *plan_tensor_map(FcChainPlan *plan, const int8_t *in, s
     return &t.map;
 }
 
-int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st) {
+int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, const GatherDst *gather,
+                    cudaStream_t st) {
     if (n == 0) return 0;
     if (n > 0x7fffff00ull) return -2;
     ChainParams p = plan->p;
     p.logits = logits;
     p.labels = labels;
     p.n = n;
+    p.n_lab_dst = p.n_log_dst = 0;
+    p.row0 = 0;
+    if (gather) {
+        if (gather->n_labels_dst > (uint32_t)kMaxGatherDst || gather->n_logits_dst > (uint32_t)kMaxGatherDst) return -5;
+        p.n_lab_dst = gather->n_labels_dst;
+        p.n_log_dst = gather->n_logits_dst;
+        p.row0 = gather->row_offset;
+        for (uint32_t d = 0; d < p.n_lab_dst; d++) p.lab_dst[d] = gather->labels_dst[d];
+        for (uint32_t d = 0; d < p.n_log_dst; d++) p.log_dst[d] = gather->logits_dst[d];
+    }
     p.n_tiles = (uint32_t)((n + kTileM - 1) / kTileM);
     const CUtensorMap *tmap_p = plan_tensor_map(plan, in, n);
     if (!tmap_p) return -3;
     const CUtensorMap &tmap = *tmap_p;
     unsigned grid = (unsigned)std::min<uint32_t>(p.n_tiles, (uint32_t)plan->sm_count);
     long long *d_trace = nullptr;
-    const char *trace_path = plan->trace_path.empty() ? nullptr : plan->trace_path.c_str();
+    const char *trace_path = (plan->trace_path.empty() || gather) ? nullptr : plan->trace_path.c_str();   // diagnostics build path
     if (trace_path) { cudaMalloc(&d_trace, 2048 * sizeof(long long)); cudaMemset(d_trace, 0, 2048 * sizeof(long long)); }
     p.trace = d_trace;
     // Mode 2 drops the grid-dependency wait, i.e. EVERY ordering against the work enqueued before this launch on the stream
@@ -651,8 +684,8 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     if (plan->stagger_override >= 0) p.stagger_cycles = (uint32_t)plan->stagger_override;
     plan->prev_in = in; plan->prev_logits = logits; plan->prev_labels = labels; plan->prev_stream = st; plan->prev_valid = true;
     if (trace_path) {
-        if (p.n_slots == 1) fc_chain_kernel<1, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
-        else fc_chain_kernel<2, true><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+        if (p.n_slots == 1) fc_chain_kernel<1, true, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+        else fc_chain_kernel<2, true, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
     } else {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -665,8 +698,9 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = plan->overlap ? 1 : 0;
-        cudaError_t e = p.n_slots == 1 ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false>, tmap, p)
-                                       : cudaLaunchKernelEx(&cfg, fc_chain_kernel<2, false>, tmap, p);
+        const bool g = p.n_lab_dst || p.n_log_dst;
+        cudaError_t e = p.n_slots == 1 ? (g ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, false>, tmap, p))
+                                       : (g ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<2, false, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_kernel<2, false, false>, tmap, p));
         if (e != cudaSuccess) return -4;
     }
     if (trace_path) {   // diagnostics only: synchronous dump of the phase clocks

@@ -6,8 +6,6 @@
 //   * fused CNN front-end: conv,conv,pool,conv,pool per channel + ReLUNorm        (BitNetMCU_MNIST_dll.c:64-80)
 // These are the layer-by-layer path (BNM_PATH_LAYERS) and the front half of every CNN model; the fused
 // tcgen05 FC chain lives in fc_tcgen05.cu.
-#include <cstdlib>
-
 #include "kernels.h"
 
 namespace bnm {
@@ -420,13 +418,12 @@ __global__ void __launch_bounds__(kCnnThreads) k_cnn_frontend16(const int8_t *__
 }
 
 bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
-                         uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, cudaStream_t st) {
-    if (xy != 16 || channels == 0 || channels > kCnnThreads) return false;
+                         uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int frontend, int *d_err,
+                         cudaStream_t st) {
+    if (xy != 16 || channels == 0) return false;
     if (n == 0) return true;
-    {   // conv1 on the tensor cores (cnn_tcgen05.cu): opt-in until validated on hardware
-        static const int tc_version = [] { const char *e = getenv("BNM_CNN_TC"); return e ? atoi(e) : 0; }();
-        if (tc_version && launch_cnn_frontend_tc(images, w1, w2, w3, channels, xy, features, feat_stride, n, sm_count, nullptr, tc_version, st)) return true;
-    }
+    if (frontend != 1 && launch_cnn_frontend_tc(images, w1, w2, w3, channels, xy, features, feat_stride, n, sm_count, d_err, st)) return true;
+    if (frontend == 2 || channels > kCnnThreads) return false;
     uint32_t ipb = kCnnThreads / channels;
     size_t smem = (size_t)ipb * (64 + 224) * 4 + ipb * 4;
     size_t n_groups = (n + ipb - 1) / ipb;

@@ -8,6 +8,15 @@ namespace bnm {
 
 constexpr int kMaxFcLayers = 8;
 constexpr int kTileM = 128;  // images per MMA tile / per CTA tile of the layer kernels
+constexpr int kMaxGatherDst = 8;   // destination buffers of the fused result exchange (one box: 8 GPUs)
+
+// destinations of the fused result exchange: layout of bnm_gather (include/bitnetmcu_b200.h)
+struct GatherDst {
+    uint32_t n_labels_dst, n_logits_dst;
+    uint32_t *labels_dst[kMaxGatherDst];
+    int32_t *logits_dst[kMaxGatherDst];
+    size_t row_offset;
+};
 
 // One fully connected layer, decoded once at model build into dense int8 planes (K3 "weight pre-decode").
 struct FcLayerDev {
@@ -38,12 +47,16 @@ void launch_conv33relu(const int32_t *act, const int8_t *w, uint32_t n_w, uint32
 void launch_maxpool22(const int32_t *act, uint32_t xy, int32_t *out, size_t n, cudaStream_t st);
 // fused CNN front-end (dll.c:64-80): images int8 [n][256] -> features int8 [n][feat_stride] after ReLUNorm over C*4
 // returns false if the geometry is not the 16x16 / conv,conv,pool,conv,pool one
+// frontend: 0 = tensor-core kernel when the shape is covered, else CUDA cores; 1 = CUDA cores (k_cnn_frontend16); 2 = tensor cores only
 bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
-                         uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, cudaStream_t st);
+                         uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int frontend, int *d_err,
+                         cudaStream_t st);
+bool cnn_frontend_tc_supported(uint32_t channels, uint32_t xy);
 
-// same front-end with conv1 on tcgen05 (cnn_tcgen05.cu); false when the shape is not covered
+// same front-end with conv1 on tcgen05 and the depthwise tail fed from TMEM (cnn_tcgen05.cu); false when the shape is not
+// covered (channels not a multiple of 16, > 128, or geometry other than 16x16)
 bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
-                            uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err, int version,
+                            uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err,
                             cudaStream_t st);
 
 // input quantisation ahead of the path (test_inference.py:140-141): float [n][elems] -> int8 [n][elems]
@@ -57,6 +70,8 @@ void fc_chain_plan_destroy(FcChainPlan *p);
 // 0 plain launches, 1 programmatic dependent launch (inputs read after the previous kernel completed), 2 launches declared independent
 void fc_chain_plan_set_overlap(FcChainPlan *p, int mode);
 // images int8 [n][in_bytes] (device, 16B aligned) -> logits int32 [n][n_classes], labels uint32 [n] (may be null)
-int fc_chain_launch(FcChainPlan *p, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st);
+// gather (may be null): extra destination buffers every row is also stored to (peer memory), fused into the epilogue
+int fc_chain_launch(FcChainPlan *p, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, const GatherDst *gather,
+                    cudaStream_t st);
 
 }  // namespace bnm

@@ -65,12 +65,16 @@ def gather_rows(local, total_rows: int, group=None):
     return torch.cat([out[r * max_rows: r * max_rows + (e - b)] for r, (b, e) in enumerate(sizes)])
 
 
-def sharded_infer(infer_local: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray]], images: np.ndarray,
-                  gather: str = "logits"):
+def sharded_infer(infer_local: Callable, images, gather: str = "logits"):
     """Run `infer_local(images_shard) -> (logits, labels)` on this rank's slice of `images` and (optionally) gather.
 
     gather = "logits": every rank gets (logits [n, C], labels [n]);  "labels": only labels are exchanged
     (4 B/image instead of 4*C: the NVLink-ingest bound of SURVEY.md 8e);  "none": results stay sharded.
+
+    Device tensors stay device tensors end to end: when `infer_local` returns torch tensors (e.g. ``Engine.infer_tensor`` on
+    a CUDA shard) they go into the collective as they are and the gathered results come back as tensors on the same device --
+    no host bounce.  NumPy in, NumPy out (the gloo CPU tests; under NCCL the arrays are staged through the GPU once).
+    For the exchange fused into the kernel's epilogue (no collective at all) see ``bitnetmcu_b200.gather``.
     """
     import torch
     import torch.distributed as dist
@@ -82,10 +86,15 @@ def sharded_infer(infer_local: Callable[[np.ndarray], Tuple[np.ndarray, np.ndarr
     logits, labels = infer_local(images[b:e])
     if world == 1 or gather == "none":
         return logits, labels
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    t_lab = gather_rows(torch.from_numpy(labels.astype(np.int32)).to(dev), n)
-    all_labels = t_lab.cpu().numpy().astype(np.uint32)
-    if gather == "labels":
-        return logits, all_labels
-    t_log = gather_rows(torch.from_numpy(np.ascontiguousarray(logits)).to(dev), n)
-    return t_log.cpu().numpy(), all_labels
+    as_numpy = not torch.is_tensor(logits)
+    if as_numpy:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t_logits = torch.from_numpy(np.ascontiguousarray(logits)).to(dev)
+        t_labels = torch.from_numpy(np.ascontiguousarray(labels).astype(np.int32)).to(dev)
+    else:
+        t_logits, t_labels = logits, labels.view(torch.int32) if labels.dtype != torch.int32 else labels
+    all_labels = gather_rows(t_labels, n)
+    all_logits = gather_rows(t_logits, n) if gather == "logits" else t_logits
+    if as_numpy:
+        return all_logits.cpu().numpy(), all_labels.cpu().numpy().astype(np.uint32)
+    return all_logits, all_labels

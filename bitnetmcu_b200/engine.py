@@ -104,6 +104,18 @@ class Engine:
                                                    lab_ptr, C.c_void_p(stream)), "bnm_infer_batch_device")
 
 
+    def infer_tensor(self, images):
+        """images: torch.int8 [n, img_bytes] on this engine's GPU -> (logits torch.int32 [n, n_classes], labels torch.int32 [n]) on
+        the same GPU, asynchronous on torch's current stream (device memory end to end; plumbing for ``dist.sharded_infer``)."""
+        import torch
+        n = images.shape[0]
+        logits = torch.empty((n, self.n_classes), dtype=torch.int32, device=images.device)
+        labels = torch.empty(n, dtype=torch.int32, device=images.device)
+        if n:
+            self.infer_device(images.contiguous(), logits, labels)
+        return logits, labels
+
+
 # ---- the four reference kernels, batched (host arrays) --------------------------------------------------------
 
 def processfclayer(activations: np.ndarray, weights: np.ndarray, bits_per_weight: int, n_input: int, n_output: int,

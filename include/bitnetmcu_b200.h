@@ -83,7 +83,10 @@ enum {
     BNM_PATH_LAYERS = 1,   /* one CUDA-core (dp4a) kernel per layer + ReLUNorm kernel; any shape          */
     BNM_PATH_TCGEN05 = 2   /* fused persistent kernel: TMA -> tcgen05.mma kind::i8 -> in-TMEM ReLUNorm     */
 };
-enum { BNM_OPT_PATH = 1, BNM_OPT_NF4_EXTENSION = 2, BNM_OPT_CHUNK_IMAGES = 3, BNM_OPT_LAUNCH_OVERLAP = 4 };
+enum { BNM_OPT_PATH = 1, BNM_OPT_NF4_EXTENSION = 2, BNM_OPT_CHUNK_IMAGES = 3, BNM_OPT_LAUNCH_OVERLAP = 4, BNM_OPT_CNN_FRONTEND = 5 };
+/* BNM_OPT_CNN_FRONTEND (CNN models, the conv/pool loop of BitNetMCU_MNIST_dll.c:64-80): 0 (default) conv1 on the tensor cores
+ * (tcgen05, depthwise tail fed from TMEM) when the channel count is a multiple of 16 and <= 128, else the CUDA-core kernel;
+ * 1 CUDA-core kernel; 2 tensor-core kernel or fail.  Results are identical. */
 /* BNM_OPT_LAUNCH_OVERLAP (fused kernel, consecutive bnm_infer_batch_device calls on one stream):
  *   0  (default) plain launches, ordinary stream semantics.
  *   1  programmatic dependent launch with a grid-dependency wait: the next launch's prologue (barriers, TMEM, weights) runs
@@ -137,6 +140,31 @@ BNM_API int bnm_infer_batch(bnm_model *m, const int8_t *images, size_t n, int32_
  * (a cudaStream_t, NULL = default stream).  No host synchronisation. */
 BNM_API int bnm_infer_batch_device(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels,
                                    void *stream);
+/* Fused result exchange (the reference has none -- its caller collects one label per call,
+ * /root/reference/test_inference.py:146-150): as bnm_infer_batch_device, and the kernel's epilogue ALSO stores row i of this call
+ * at row (row_offset + i) of every destination buffer: labels uint32 [rows], logits int32 [rows][n_classes].  Destinations
+ * are device pointers valid on the model's GPU -- typically buffers of the peer GPUs of the box mapped through CUDA IPC
+ * (bnm_ipc_export / bnm_ipc_open) or same-process P2P (bnm_enable_peer_access), so that the all-gather of the batch-sharded
+ * results rides under the compute over NVLink instead of running as a collective after it.  Visibility at the destination
+ * follows stream completion of this call on the source plus whatever cross-rank synchronisation the caller uses.
+ * Only the fused tcgen05 path supports it. */
+#define BNM_MAX_GATHER_DST 8
+typedef struct bnm_gather {
+    uint32_t n_labels_dst, n_logits_dst;
+    uint32_t *labels_dst[BNM_MAX_GATHER_DST];
+    int32_t *logits_dst[BNM_MAX_GATHER_DST];   /* 8-byte aligned */
+    size_t row_offset;
+} bnm_gather;
+BNM_API int bnm_infer_batch_device_gather(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels,
+                                          const bnm_gather *gather, void *stream);
+/* device memory that can be exported to the other processes of the box (cudaMalloc), CUDA IPC handles (64 bytes) */
+BNM_API int bnm_device_alloc(int device, size_t bytes, void **out);
+BNM_API void bnm_device_free(void *p);
+BNM_API int bnm_ipc_export(const void *dev_ptr, void *handle64);
+BNM_API int bnm_ipc_open(int device, const void *handle64, void **out);
+BNM_API int bnm_ipc_close(void *p);
+BNM_API int bnm_enable_peer_access(int device, int peer);   /* same-process multi-GPU */
+
 /* number of kernels bnm_infer_batch_device launches for n images with the current options */
 BNM_API int bnm_infer_launch_count(const bnm_model *m, size_t n);
 

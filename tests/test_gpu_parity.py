@@ -21,9 +21,21 @@ def lib(built):
     return l
 
 
-def _engine(name, path, nf4=False):
+def _engine(name, path, nf4=False, cnn_frontend=None):
+    from bitnetmcu_b200 import _lib
     from bitnetmcu_b200.engine import Engine
-    return Engine(load_model(name), device=0, path=path, nf4_extension=nf4)
+    e = Engine(load_model(name), device=0, path=path, nf4_extension=nf4)
+    if cnn_frontend is not None:
+        e.set_option(_lib.OPT_CNN_FRONTEND, cnn_frontend)
+    return e
+
+
+def _frontends(model):
+    """CNN models run once per front-end kernel (BNM_OPT_CNN_FRONTEND): CUDA cores and conv1-on-tcgen05; FC models once."""
+    from bitnetmcu_b200 import _lib
+    if model.model_class != 1:
+        return [None]
+    return [_lib.CNN_CUDA_CORES, _lib.CNN_TENSOR_CORES] if model.channels % 16 == 0 else [_lib.CNN_CUDA_CORES]
 
 
 def _paths(name):
@@ -48,24 +60,26 @@ def _rand_images(n, seed=0):
 @pytest.mark.parametrize("name", model_names())
 def test_model_matches_golden_and_oracle(lib, oracle, golden, digits, name, path):
     from bitnetmcu_b200 import _lib
-    e = _engine(name, _lib.PATH_LAYERS if path == "layers" else _lib.PATH_TCGEN05)
-    assert e.active_path == (_lib.PATH_LAYERS if path == "layers" else _lib.PATH_TCGEN05)
-    imgs, _ = digits
-    lo, la = e.infer(imgs)
-    assert np.array_equal(lo, golden[name + "/digits_logits"]), "digits logits differ from the reference"
-    assert np.array_equal(la, golden[name + "/digits_labels"])
-    xs = oracle.xorshift_images(256)
-    lo, la = e.infer(xs)
-    assert np.array_equal(lo, golden[name + "/xs_logits"])
-    assert np.array_equal(la, golden[name + "/xs_labels"])
-    # ragged random batch (not a multiple of the 128-image tile), full compare with the oracle
+    model = load_model(name)
     n = 5000 + 37
     r = _rand_images(n, seed=len(name))
-    lo, la = e.infer(r)
-    oo, ol = oracle.infer(load_model(name), r)
-    assert np.array_equal(lo, oo), f"{np.argwhere(lo != oo)[:5]}"
-    assert np.array_equal(la, ol)
-    e.close()
+    oo, ol = oracle.infer(model, r)
+    for fe in _frontends(model):
+        e = _engine(name, _lib.PATH_LAYERS if path == "layers" else _lib.PATH_TCGEN05, cnn_frontend=fe)
+        assert e.active_path == (_lib.PATH_LAYERS if path == "layers" else _lib.PATH_TCGEN05)
+        imgs, _ = digits
+        lo, la = e.infer(imgs)
+        assert np.array_equal(lo, golden[name + "/digits_logits"]), f"digits logits differ from the reference (front-end {fe})"
+        assert np.array_equal(la, golden[name + "/digits_labels"])
+        xs = oracle.xorshift_images(256)
+        lo, la = e.infer(xs)
+        assert np.array_equal(lo, golden[name + "/xs_logits"]), f"front-end {fe}"
+        assert np.array_equal(la, golden[name + "/xs_labels"])
+        # ragged random batch (not a multiple of the 128-image tile), full compare with the oracle
+        lo, la = e.infer(r)
+        assert np.array_equal(lo, oo), f"front-end {fe}: {np.argwhere(lo != oo)[:5]}"
+        assert np.array_equal(la, ol)
+        e.close()
 
 
 @pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 255, 257, 1000])
@@ -74,14 +88,15 @@ def test_edge_batch_sizes(lib, oracle, n):
     for name in ("fc", "cnn_48"):
         m = load_model(name)
         for path in (_lib.PATH_LAYERS, _lib.PATH_TCGEN05):
-            e = _engine(name, path)
-            imgs = _rand_images(n, seed=n)
-            lo, la = e.infer(imgs)
-            assert lo.shape == (n, m.n_classes)
-            if n:
-                oo, ol = oracle.infer(m, imgs)
-                assert np.array_equal(lo, oo) and np.array_equal(la, ol)
-            e.close()
+            for fe in _frontends(m):
+                e = _engine(name, path, cnn_frontend=fe)
+                imgs = _rand_images(n, seed=n)
+                lo, la = e.infer(imgs)
+                assert lo.shape == (n, m.n_classes)
+                if n:
+                    oo, ol = oracle.infer(m, imgs)
+                    assert np.array_equal(lo, oo) and np.array_equal(la, ol), (name, path, fe)
+                e.close()
 
 
 def test_survey_kat_on_gpu(lib, oracle):
@@ -358,10 +373,13 @@ def test_extreme_weights_cnn(lib, oracle):
             l.weights = w
     imgs = _extreme_images()
     want_logits, want_labels = oracle.infer(base, imgs)
-    e = Engine(base)
-    lo_, la_ = e.infer(imgs)
-    assert np.array_equal(lo_, want_logits) and np.array_equal(la_, want_labels)
-    e.close()
+    from bitnetmcu_b200 import _lib
+    for fe in _frontends(base):
+        e = Engine(base)
+        e.set_option(_lib.OPT_CNN_FRONTEND, fe)
+        lo_, la_ = e.infer(imgs)
+        assert np.array_equal(lo_, want_logits) and np.array_equal(la_, want_labels), fe
+        e.close()
 
 
 def test_quantize_images_matches_numpy(lib):
@@ -497,3 +515,36 @@ def test_launch_overlap_mode2_reused_buffers_keep_stream_order(lib, oracle):
     for (gl, gb), (wl, wb) in zip(got, want):
         assert np.array_equal(gl.cpu().numpy(), wl) and np.array_equal(gb.cpu().numpy().astype(np.uint32), wb)
     e.close()
+
+
+@pytest.mark.parametrize("channels", [16, 32, 48, 64, 80, 96, 112, 128])
+def test_cnn_frontends_agree_for_every_channel_count(lib, oracle, channels):
+    """Random conv weights for every channel count the tensor-core front-end takes (multiples of 16 up to 128: tiles that
+    straddle images for C = 48 / 80 / 96, eight images per tile for C = 16) against the oracle, both front-end kernels, ragged
+    batch sizes around the group size."""
+    from bitnetmcu_b200 import _lib, model as M, pack as P
+    from bitnetmcu_b200.engine import Engine
+    rng = np.random.default_rng(channels)
+    layers = []
+    for name, xy in (("L2", 16), ("L4", 14)):
+        layers.append(M.Layer(kind=M.LAYER_CONV33, name=name, bitperweight=8, n_in=xy, n_out=channels, in_channels=1 if xy == 16 else channels,
+                              groups=1 if xy == 16 else channels, weights=rng.integers(-128, 128, size=channels * 9).astype(np.int8)))
+    layers.append(M.Layer(kind=M.LAYER_MAXPOOL22, name="L6", n_in=12, n_out=6))
+    layers.append(M.Layer(kind=M.LAYER_CONV33, name="L7", bitperweight=8, n_in=6, n_out=channels, in_channels=channels, groups=channels,
+                          weights=rng.integers(-128, 128, size=channels * 9).astype(np.int8)))
+    layers.append(M.Layer(kind=M.LAYER_MAXPOOL22, name="L9", n_in=4, n_out=2))
+    fc = P.random_fc_model(M.ENC_4BITSYM, (channels * 4, 64, 10), seed=channels)
+    for i, l in enumerate(fc.layers):
+        l.name = f"L{11 + 2 * i}"
+        layers.append(l)
+    m = M.Model(model_class=M.MODEL_CNNMNIST, layers=layers)
+    m.validate()
+    for n in (1, 7, 8, 9, 300, 4099):
+        imgs = _rand_images(n, seed=n + channels)
+        want, want_lab = oracle.infer(m, imgs)
+        for fe in (_lib.CNN_CUDA_CORES, _lib.CNN_TENSOR_CORES):
+            e = Engine(m)
+            e.set_option(_lib.OPT_CNN_FRONTEND, fe)
+            lo, la = e.infer(imgs)
+            assert np.array_equal(lo, want) and np.array_equal(la, want_lab), (channels, n, fe, np.argwhere(lo != want)[:4])
+            e.close()
