@@ -85,7 +85,8 @@ struct bnm_model {
     // test_inference.py:146-150): pinned staging buffers, one stream, one synchronisation
     int8_t *small_h_in = nullptr, *small_d_in = nullptr;     // [kSmallBatch][img_bytes]
     int32_t *small_h_out = nullptr, *small_d_out = nullptr;  // logits [n][n_classes] then labels [n]
-    int small_zero_copy = 0;   // 0: H2D + D2H copies; 1: the kernel writes results straight into mapped pinned host memory; 2: ... and reads the images from it
+    int small_zero_copy = 1;   // 0: H2D + D2H copies; 1 (default, measured fastest: 14.3 vs 20.1 / 16.8 us per call): the kernel writes results
+                               // straight into mapped pinned host memory; 2: ... and reads the images from it (TMA over PCIe)
 };
 static const size_t kSmallBatch = 1024;
 
