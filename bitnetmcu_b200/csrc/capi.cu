@@ -68,6 +68,8 @@ struct bnm_model {
     size_t chunk_images = 1 << 16;   // host pipeline chunk
     int launch_overlap = 0;
     int cnn_frontend = 0;            // BNM_OPT_CNN_FRONTEND
+    bool conv3_fits_u16 = false;     // static range of conv3's inputs for this model's weights (cnn_conv3_fits_u16)
+    std::vector<int8_t> h_conv[3];   // host copies of the conv weights (range analysis)
     int *d_err = nullptr;            // error word of the bounded device-side waits
     // fused plan
     FcChainPlan *plan = nullptr;
@@ -242,6 +244,7 @@ extern "C" int bnm_model_create(int model_class, const bnm_layer *layers, uint32
             else if (L.n_out != m->channels) { rc = fail(BNM_E_UNSUPPORTED, "conv layers must share the channel count (dll.c:66)"); break; }
             if (cudaMalloc(&m->d_conv[n_conv], (size_t)L.n_out * 9) != cudaSuccess) { rc = fail(BNM_E_CUDA, "cudaMalloc failed"); break; }
             cudaMemcpy(m->d_conv[n_conv], L.weights, (size_t)L.n_out * 9, cudaMemcpyHostToDevice);
+            m->h_conv[n_conv].assign(static_cast<const int8_t *>(L.weights), static_cast<const int8_t *>(L.weights) + (size_t)L.n_out * 9);
             n_conv++;
         } else if (L.kind == BNM_LAYER_MAXPOOL22) {
             front.push_back(L.kind);
@@ -259,6 +262,7 @@ extern "C" int bnm_model_create(int model_class, const bnm_layer *layers, uint32
         else {
             uint32_t f = ((m->xy0 - 4) / 2 - 2) / 2;   // 16 -> 2
             m->feat_stride = round_up(m->channels * f * f, 16);
+            m->conv3_fits_u16 = cnn_conv3_fits_u16(m->h_conv[0].data(), m->h_conv[1].data(), m->channels);
         }
     }
     if (rc == 0 && model_class == BNM_MODEL_FCMNIST && !front.empty()) rc = fail(BNM_E_ARG, "MODEL_FCMNIST with conv/pool layers");
@@ -402,7 +406,7 @@ static int run_fc_layers(bnm_model *m, const int8_t *in, uint32_t in_stride, siz
 // CNN front-end into m->d_feat (int8 [n][feat_stride])
 static int run_cnn_front(bnm_model *m, const int8_t *images, size_t n, cudaStream_t st) {
     if (launch_cnn_frontend(images, m->d_conv[0], m->d_conv[1], m->d_conv[2], m->channels, m->xy0, m->d_feat, m->feat_stride, n,
-                            m->sm_count, m->cnn_frontend, m->d_err, st))
+                            m->sm_count, m->cnn_frontend, m->d_err, m->conv3_fits_u16, st))
         return 0;
     return fail(BNM_E_UNSUPPORTED, "CNN front-end: %u channels at %ux%u not supported by the selected kernel (the reference hard-codes 16x16, dll.c:68)",
                 m->channels, m->xy0, m->xy0);
@@ -747,6 +751,72 @@ extern "C" int bnm_quantize_images(const float *images, size_t n, uint32_t elems
     launch_quantize_images(in.as<float>(), elems, q.as<int8_t>(), n, 0);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpy(out, q.p, n * (size_t)elems, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// -----------------------------------------------------------------------------------------------
+// Emulation mode: QuantizedModel.inference_quantized of the reference (BitNetMCU.py:420-535) on the GPU --
+// float images in, float64 "logits" out, with the EMULATOR's normalisation rules (power-of-two rescale to max <= 127 with
+// round-half-even for BitLinear, per-image renormalisation of every conv output) instead of the C engine's.  It reuses the
+// engine's integer kernels (decoded weights, dp4a layers, conv / pool); weight levels are the engine's integers divided by
+// level_scale (2 for 2bitsym / 4bitsym), so every intermediate is an exact dyadic rational and the result equals NumPy's.
+// -----------------------------------------------------------------------------------------------
+static int level_shift_of(int32_t enc) { return (enc == BNM_ENC_2BITSYM || enc == BNM_ENC_4BITSYM) ? 1 : 0; }
+
+extern "C" int bnm_emulate_inference_quantized(bnm_model *m, const float *images, size_t n, double *logits) {
+    if (!m || (n && (!images || !logits))) return fail(BNM_E_ARG, "bnm_emulate_inference_quantized: null argument");
+    if (n == 0) return 0;
+    CU_TRY(cudaSetDevice(m->device));
+    const bool cnn = m->model_class == BNM_MODEL_CNNMNIST;
+    const uint32_t C = m->channels, elems = m->img_bytes;
+    const size_t chunk = std::min<size_t>(n, cnn ? 2048 : 65536);
+    const size_t nl = m->fc.size();
+    uint32_t max_nout = 1, max_kpad = round_up(std::max(m->img_bytes, m->feat_stride), 32);
+    for (auto &L : m->fc) { max_nout = std::max(max_nout, L.n_out); max_kpad = std::max(max_kpad, L.k_pad); }
+    DevBuf d_f, d_q, d_acc, d_a0, d_a1, d_p0, d_p1;
+    if (d_f.alloc(chunk * elems * 4) || d_q.alloc(chunk * elems) || d_acc.alloc(chunk * (size_t)max_nout * 4) || d_a0.alloc(chunk * (size_t)max_kpad) ||
+        d_a1.alloc(chunk * (size_t)max_kpad) || (cnn && (d_p0.alloc(chunk * C * 256 * 4) || d_p1.alloc(chunk * C * 256 * 4))))
+        return fail(BNM_E_CUDA, "cudaMalloc failed (emulation scratch)");
+    CU_TRY(cudaMemset(d_a0.p, 0, chunk * (size_t)max_kpad));
+    CU_TRY(cudaMemset(d_a1.p, 0, chunk * (size_t)max_kpad));
+    std::vector<int32_t> h_acc(chunk * (size_t)m->n_classes);
+    cudaStream_t st = 0;
+    for (size_t b = 0; b < n; b += chunk) {
+        const size_t nb = std::min(chunk, n - b);
+        CU_TRY(cudaMemcpy(d_f.p, images + b * elems, nb * elems * 4, cudaMemcpyHostToDevice));
+        launch_quantize_images(d_f.as<float>(), elems, d_q.as<int8_t>(), nb, st);   // BitNetMCU.py:435-436
+        const int8_t *act = d_q.as<int8_t>();
+        uint32_t stride = elems;
+        if (cnn) {
+            // conv (ReLU, no shift) -> per-image renormalisation, pools in between (BitNetMCU.py:459-526), planes [(image, channel)][xy*xy]
+            int32_t *p0 = d_p0.as<int32_t>(), *p1 = d_p1.as<int32_t>();
+            launch_expand_image(d_q.as<int8_t>(), p0, C, 256, nb, st);
+            launch_conv33relu(p0, m->d_conv[0], C, 16, 0, p1, nb * C, st);
+            launch_conv_renorm(p1, C * 196, nb, st);
+            launch_conv33relu(p1, m->d_conv[1], C, 14, 0, p0, nb * C, st);
+            launch_conv_renorm(p0, C * 144, nb, st);
+            launch_maxpool22(p0, 12, p1, nb * C, st);
+            launch_conv33relu(p1, m->d_conv[2], C, 6, 0, p0, nb * C, st);
+            launch_conv_renorm(p0, C * 16, nb, st);
+            launch_maxpool22(p0, 4, p1, nb * C, st);
+            launch_i32_to_i8(p1, C * 4, d_a1.as<int8_t>(), m->feat_stride, nb, st);   // flatten (C, 2, 2) -> features (BitNetMCU.py:443-445)
+            act = d_a1.as<int8_t>();
+            stride = m->feat_stride;
+        }
+        for (size_t l = 0; l < nl; l++) {
+            if (!launch_fc_dp4a(act, stride, m->fc[l], d_acc.as<int32_t>(), nb, st)) return fail(BNM_E_UNSUPPORTED, "FC layer %zu too wide for the layer kernel", l);
+            if (l + 1 == nl) break;   // no renormalisation for the last layer (BitNetMCU.py:528-530)
+            int8_t *next = (l & 1) ? d_a1.as<int8_t>() : d_a0.as<int8_t>();   // CNN features sit in d_a1 and are dead once layer 0 has run
+            const uint32_t next_stride = m->fc[l + 1].k_pad;
+            launch_relunorm_emul(d_acc.as<int32_t>(), m->fc[l].n_out, level_shift_of(m->fc[l].enc), next, next_stride, nb, st);
+            act = next;
+            stride = next_stride;
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpy(h_acc.data(), d_acc.p, nb * (size_t)m->n_classes * 4, cudaMemcpyDeviceToHost));
+        const double inv = 1.0 / (double)(1 << level_shift_of(m->fc[nl - 1].enc));
+        for (size_t i = 0; i < nb * (size_t)m->n_classes; i++) logits[b * m->n_classes + i] = (double)h_acc[i] * inv;
+    }
     return 0;
 }
 

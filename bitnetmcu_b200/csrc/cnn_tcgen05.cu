@@ -39,7 +39,7 @@
 
 namespace bnm {
 
-constexpr uint32_t kCnnTcThreads = 320;          // 2 consumer warpgroups (8 warps) + 2 producer / MMA-issuer warps
+constexpr uint32_t kCnnTcThreads = 384;          // 2 consumer warpgroups (8 warps) + 2 producer pairs (4 warps, one per SM sub-partition)
 constexpr uint32_t kPlaneBytes = 224 * 16;       // im2col plane of one image: 14 rows x 16 positions x 16 bytes
 constexpr uint32_t kHalfCols = 112;              // accumulator half: conv1 rows 0..6 / 7..13, 16 columns each
 
@@ -68,34 +68,60 @@ __device__ __forceinline__ uint32_t pack_relu_u16(int hi, int lo) {
     return d;
 }
 
+// (uint16, uint16) . (int8, int8) + c: pooled conv2 outputs reach 65535, beyond the int16 range of __dp2a_lo(int, int, int)
+__device__ __forceinline__ int dp2a_u16_s8(uint32_t a, int b, int c) {
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // per-channel weights of the depthwise tail, 16 words
 struct CnnTailW {
     int w01[3];        // conv2 kernel row r: (w[r][0], w[r][1]) as int8 pair in the low two bytes
     int wva, wvb;      // third column, vertical pairs: (w[1][2], w[2][2]) for the upper row of a pair, (w[0][2], w[1][2]) for the lower
     int wsa, wsb;      // third column, single taps: (w[0][2], 0) and (w[2][2], 0)
-    int k3[9];         // conv3
+    int k3[9];         // conv3: scalars, or -- kConv3Packed -- k3[0..6] = the same seven pair words for conv3's kernel
 };
 
 // One tile of one consumer thread: conv1 sums from TMEM -> 4 raw features (before ReLUNorm) of this (image, channel).
 // tm = TMEM address of this thread's lane quarter at the warpgroup's first accumulator column.
+// kConv3Packed: conv3's inputs (pooled conv2 outputs) are known to fit 16 bits for this model's weights (static bound, checked on
+// the host), so conv3 runs on IDP.2A like conv2 (80 instead of 144 FMA-pipe instructions); otherwise int32 x int8 IMADs.
+// kFromSmem (tools/cnn_tail_bench.cu only): the conv1 sums are read from shared memory at byte address tm + 64 * row instead of
+// TMEM and no barrier is touched, so the arithmetic of the tail can be timed in isolation.
+template <bool kConv3Packed, bool kFromSmem = false>
 __device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, uint32_t bar_full1, uint32_t bar_free0,
                                               uint32_t bar_free1, uint32_t parity, const CnnTailW &W, int (&f)[4], int *err) {
+    auto load_row = [&](int y, uint32_t (&r)[16]) {
+        if (kFromSmem) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[4 * q]), "=r"(r[4 * q + 1]), "=r"(r[4 * q + 2]), "=r"(r[4 * q + 3])
+                             : "r"(tm + 64 * y + 16 * q));
+        } else {
+            tmem_ld_x16(tm + y * 16, r);
+        }
+    };
+    auto wait_row = [&](uint32_t (&r)[16]) { if (!kFromSmem) tmem_ld_wait_x16(r); };
     uint32_t E[14][7], O[14][7];   // conv1 rows as int16 pairs: E[y][j] = (v[2j], v[2j+1]), O[y][j] = (v[2j+1], v[2j+2]); 4 rows live
     int pl[6][6];                  // pooled conv2 rows (3 live)
     int c3e[4];
+    uint32_t PE[6][3], PO[6][3];   // kConv3Packed: pooled rows as uint16 pairs
     uint32_t cur[16], nxt[16];
-    mbar_wait_a(bar_full0, parity, err, 11);
-    tc_fence_after();
-    tmem_ld_x16(tm, cur);
-    tmem_ld_wait_x16(cur);
+    if (!kFromSmem) {
+        mbar_wait_a(bar_full0, parity, err, 11);
+        tc_fence_after();
+    }
+    load_row(0, cur);
+    wait_row(cur);
 #pragma unroll
     for (int y = 0; y < 14; y++) {
         if (y + 1 < 14) {
-            if (y + 1 == 7) {
+            if (y + 1 == 7 && !kFromSmem) {
                 mbar_wait_a(bar_full1, parity, err, 12);
                 tc_fence_after();
             }
-            tmem_ld_x16(tm + (y + 1) * 16, nxt);   // prefetch the next conv1 row while this one is processed
+            load_row(y + 1, nxt);   // prefetch the next conv1 row while this one is processed
         }
         {   // ReLU >> 4 of conv1 (inference.c:261-272) and int16 pairing
             int t[14];
@@ -132,31 +158,65 @@ __device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, u
                 pl[p][j] = max(__vimax3_s32_relu(a[0], a[1], b[0]), b[1]) >> 4;   // maxpool, then ReLU >> 4 (monotone: same result)
             }
 #undef BNM_P
-            if (p >= 2) {
-                const int q = p - 2;   // conv3 output row
-                int u[4];
+            if (!kConv3Packed) {
+                if (p >= 2) {
+                    const int q = p - 2;   // conv3 output row
+                    int u[4];
 #pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    int s = 0;
+                    for (int x = 0; x < 4; x++) {
+                        int s = 0;
 #pragma unroll
-                    for (int dr = 0; dr < 3; dr++)
+                        for (int dr = 0; dr < 3; dr++)
 #pragma unroll
-                        for (int dc = 0; dc < 3; dc++) s += W.k3[3 * dr + dc] * pl[q + dr][x + dc];
-                    u[x] = s;
+                            for (int dc = 0; dc < 3; dc++) s += W.k3[3 * dr + dc] * pl[q + dr][x + dc];
+                        u[x] = s;
+                    }
+                    if ((q & 1) == 0) {
+#pragma unroll
+                        for (int x = 0; x < 4; x++) c3e[x] = u[x];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2; j++)
+                            f[(q >> 1) * 2 + j] = max(__vimax3_s32_relu(c3e[2 * j], c3e[2 * j + 1], u[2 * j]), u[2 * j + 1]) >> 4;
+                    }
                 }
-                if ((q & 1) == 0) {
+            } else {
+                // pooled row p as uint16 pairs, then conv3 exactly like conv2: output rows (0,1) after pooled row 3, (2,3) after row 5
 #pragma unroll
-                    for (int x = 0; x < 4; x++) c3e[x] = u[x];
-                } else {
+                for (int j = 0; j < 3; j++) PE[p][j] = __byte_perm((uint32_t)pl[p][2 * j], (uint32_t)pl[p][2 * j + 1], 0x5410);
 #pragma unroll
-                    for (int j = 0; j < 2; j++)
-                        f[(q >> 1) * 2 + j] = max(__vimax3_s32_relu(c3e[2 * j], c3e[2 * j + 1], u[2 * j]), u[2 * j + 1]) >> 4;
+                for (int j = 0; j < 2; j++) PO[p][j] = __byte_perm((uint32_t)pl[p][2 * j + 1], (uint32_t)pl[p][2 * j + 2], 0x5410);
+                PO[p][2] = (uint32_t)pl[p][5];
+                if (p == 3 || p == 5) {
+                    const int Q0 = p - 3, Q1 = p - 2, Q2 = p - 1, Q3 = p;
+#define BNM_Q(r, x) (((x) & 1) ? PO[r][(x) >> 1] : PE[r][(x) >> 1])
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        int a[2], b[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int x = 2 * j + e;
+                            const int v = (int)__byte_perm(BNM_Q(Q1, x + 2), BNM_Q(Q2, x + 2), 0x5410);
+                            int s = dp2a_u16_s8(BNM_Q(Q0, x), W.k3[0], 0);
+                            s = dp2a_u16_s8(BNM_Q(Q1, x), W.k3[1], s);
+                            s = dp2a_u16_s8(BNM_Q(Q2, x), W.k3[2], s);
+                            s = dp2a_u16_s8((uint32_t)v, W.k3[3], s);
+                            a[e] = dp2a_u16_s8(BNM_Q(Q0, x + 2), W.k3[5], s);
+                            int u = dp2a_u16_s8(BNM_Q(Q1, x), W.k3[0], 0);
+                            u = dp2a_u16_s8(BNM_Q(Q2, x), W.k3[1], u);
+                            u = dp2a_u16_s8(BNM_Q(Q3, x), W.k3[2], u);
+                            u = dp2a_u16_s8((uint32_t)v, W.k3[4], u);
+                            b[e] = dp2a_u16_s8(BNM_Q(Q3, x + 2), W.k3[6], u);
+                        }
+                        f[(p == 5 ? 2 : 0) + j] = max(__vimax3_s32_relu(a[0], a[1], b[0]), b[1]) >> 4;
+                    }
+#undef BNM_Q
                 }
             }
         }
         if (y + 1 < 14) {
-            tmem_ld_wait_x16(nxt);
-            if (y + 1 == 6 || y + 1 == 13) {   // the last row of an accumulator half is in registers: the half may be overwritten
+            wait_row(nxt);
+            if (!kFromSmem && (y + 1 == 6 || y + 1 == 13)) {   // the last row of an accumulator half is in registers: the half may be overwritten
                 tc_fence_before();
                 mbar_arrive_a(y + 1 == 6 ? bar_free0 : bar_free1);
             }
@@ -166,9 +226,11 @@ __device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, u
     }
 }
 
+template <bool kConv3Packed>
 __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __grid_constant__ CnnTcParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[2][2], bar_free[2][2];   // [warpgroup][accumulator half]
+    __shared__ __align__(8) uint64_t bar_group[2];                     // [warpgroup]: a group's per-image maxima are published
     __shared__ uint32_t tmem_base_s;
     const uint32_t t = threadIdx.x, lane = t & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
@@ -181,6 +243,8 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
         for (int g = 0; g < 2; g++)
 #pragma unroll
             for (int h = 0; h < 2; h++) { mbar_init(&bar_full[g][h], 1); mbar_init(&bar_free[g][h], 128); }
+        mbar_init(&bar_group[0], 128);
+        mbar_init(&bar_group[1], 128);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc<512>(&tmem_base_s);
@@ -206,8 +270,15 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
             o[0] = pair(b[0], b[1]); o[1] = pair(b[3], b[4]); o[2] = pair(b[6], b[7]);
             o[3] = pair(b[5], b[8]); o[4] = pair(b[2], b[5]);
             o[5] = pair(b[2], 0); o[6] = pair(b[8], 0);
+            if (kConv3Packed) {
+                o[7] = pair(c[0], c[1]); o[8] = pair(c[3], c[4]); o[9] = pair(c[6], c[7]);
+                o[10] = pair(c[5], c[8]); o[11] = pair(c[2], c[5]);
+                o[12] = pair(c[2], 0); o[13] = pair(c[8], 0);
+                o[14] = o[15] = 0;
+            } else {
 #pragma unroll
-            for (int k = 0; k < 9; k++) o[7 + k] = c[k];
+                for (int k = 0; k < 9; k++) o[7 + k] = c[k];
+            }
         }
         int *imax = reinterpret_cast<int *>(base + P.off_imax);
         for (uint32_t i = t; i < 2 * 3 * 8; i += kCnnTcThreads) imax[i] = 0;
@@ -219,57 +290,68 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp >= 8) {
-        // ======================= producer + MMA issuer of warpgroup g =======================
-        const uint32_t g = warp - 8;
+        // ======================= producer pair of warpgroup g: warps 8 + g (also the MMA issuer) and 10 + g =======================
+        // Four helper warps, one per SM sub-partition, so that every sub-partition carries the same load (two consumer warps + half
+        // a producer): the consumers of a warpgroup advance in lockstep through the accumulator barriers, and a sub-partition that
+        // also hosted a whole producer used to set the pace for all four.  The two warps of a pair split a group's im2col tasks
+        // and meet at a 64-thread named barrier (id 1 + g).
+        const uint32_t g = (warp - 8) & 1, helper = (warp - 8) >> 1, lane64 = lane + 32 * helper;
         const bool leader = elect_one();
         uint32_t *s_img = reinterpret_cast<uint32_t *>(base + P.off_img + g * (8 * 256 + 64));
-        const uint32_t n_ld = (G * 16 + 31) / 32;   // 16-byte loads per lane and group (<= 4)
+        const uint32_t n_ld = (G * 16 + 63) / 64;   // 16-byte loads per lane and group (<= 2)
         const uint32_t idesc = make_idesc_i8(128, kHalfCols);
         const uint32_t a_base = smem_u32(base + P.off_a);
         uint32_t free_phase = 0;   // one bit per half; a fresh barrier passes a wait on parity 1
-        uint4 img_regs[4];
+        uint4 img_regs[2];
         auto load_group = [&](size_t grp) {   // global -> registers (latency hidden behind the previous group's work)
 #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
+            for (uint32_t k = 0; k < 2; k++) {
                 img_regs[k] = make_uint4(0, 0, 0, 0);
-                const uint32_t idx = k * 32 + lane;   // uint4 index inside the group: image = idx / 16
+                const uint32_t idx = k * 64 + lane64;   // uint4 index inside the group: image = idx / 16
                 if (k < n_ld && idx < G * 16 && grp * G + idx / 16 < P.n)
                     img_regs[k] = reinterpret_cast<const uint4 *>(P.images)[grp * G * 16 + idx];
             }
         };
-        auto build_group = [&](uint32_t buf) {   // registers -> s_img -> im2col planes of buffer buf
-            __syncwarp();
+        auto build_group = [&](uint32_t buf) {   // registers -> s_img -> im2col planes of buffer buf, both warps of the pair
 #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
-                const uint32_t idx = k * 32 + lane;
+            for (uint32_t k = 0; k < 2; k++) {
+                const uint32_t idx = k * 64 + lane64;
                 if (k < n_ld && idx < G * 16) reinterpret_cast<uint4 *>(s_img)[idx] = img_regs[k];
             }
-            __syncwarp();
+            named_bar_sync(1 + g, 64);   // the group's images are staged
             uint8_t *bbuf = base + P.off_b + (g * 2 + buf) * P.b_buf_bytes;
+            // one task = four consecutive positions (y, 4 xg .. 4 xg + 3) of one image: six shared-memory words (two per image row)
+            // feed four 16-byte im2col rows; 56 tasks per image (14 rows x 4 column groups, the last group holds x = 12, 13 only)
 #pragma unroll 1
-            for (uint32_t idx = lane; idx < G * 196; idx += 32) {
-                const uint32_t im = idx / 196, pos = idx - im * 196, y = pos / 14, x = pos - y * 14;
-                const uint32_t *row = s_img + im * 64 + y * 4 + (x >> 2);
-                const uint32_t sh = 8 * (x & 3);
-                const uint32_t wa = __funnelshift_r(row[0], row[1], sh), wb = __funnelshift_r(row[4], row[5], sh),
-                               wc = __funnelshift_r(row[8], row[9], sh);
-                // taps in the order of w1[c][0..8]: (a0 a1 a2 b0 | b1 b2 c0 c1 | c2 . . . | . . . .); bytes 9..15 meet zeros in A
-                uint4 q;
-                q.x = __byte_perm(wa, wb, 0x4210);
-                q.y = __byte_perm(wb, wc, 0x5421);
-                q.z = wc >> 16;
-                q.w = 0;
-                *reinterpret_cast<uint4 *>(bbuf + im * kPlaneBytes + (y * 16 + x) * 16) = q;
+            for (uint32_t task = lane64; task < G * 56; task += 64) {
+                const uint32_t im = task / 56, rem = task - im * 56, y = rem >> 2, xg = rem & 3;
+                const uint32_t *row = s_img + im * 64 + y * 4 + xg;
+                const uint32_t a0 = row[0], a1 = row[1], b0 = row[4], b1 = row[5], c0 = row[8], c1 = row[9];
+                uint8_t *dst = bbuf + im * kPlaneBytes + (y * 16 + xg * 4) * 16;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < 2 || xg < 3) {
+                        const uint32_t wa = i ? __funnelshift_r(a0, a1, 8 * i) : a0, wb = i ? __funnelshift_r(b0, b1, 8 * i) : b0,
+                                       wc = i ? __funnelshift_r(c0, c1, 8 * i) : c0;
+                        // taps in the order of w1[c][0..8]: (a0 a1 a2 b0 | b1 b2 c0 c1 | c2 . . . | . . . .); bytes 9..15 meet zeros in A
+                        uint4 q;
+                        q.x = __byte_perm(wa, wb, 0x4210);
+                        q.y = __byte_perm(wb, wc, 0x5421);
+                        q.z = wc >> 16;
+                        q.w = 0;
+                        *reinterpret_cast<uint4 *>(dst + 16 * i) = q;
+                    }
+                }
             }
             fence_proxy_async_smem();   // the MMAs (async proxy) read what these generic-proxy stores wrote
-            __syncwarp();
+            named_bar_sync(1 + g, 64);   // both halves of the build are done (and s_img may be overwritten)
         };
-        auto issue_tile = [&](uint32_t buf, uint32_t tau) {
+        auto issue_tile = [&](uint32_t buf, uint32_t tau) {   // issuer warp only
             const uint32_t i0 = (tau * 128) / C, i1 = (tau * 128 + 127) / C;
             const uint32_t n_k = (i1 - i0 + 2) / 2;   // K-steps of 32 bytes = two image slots
             const uint32_t b_base = smem_u32(base + P.off_b + (g * 2 + buf) * P.b_buf_bytes) + i0 * kPlaneBytes;
             for (uint32_t h = 0; h < 2; h++) {
-                mbar_wait(&bar_free[g][h], ((free_phase >> h) & 1) ^ 1, P.err, 13);
+                mbar_wait_relaxed(&bar_free[g][h], ((free_phase >> h) & 1) ^ 1, P.err, 13);
                 free_phase ^= 1u << h;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + g * 224 + h * kHalfCols;
@@ -292,14 +374,15 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
             if (j + stride < P.n_groups) load_group(j + stride);
         }
         for (; j < P.n_groups; j += stride, buf ^= 1) {
-            issue_tile(buf, 0);
+            if (!helper) issue_tile(buf, 0);
             // Every MMA of the group before this one has completed (its last accumulator halves were drained before the waits
-            // above passed): the other im2col buffer is free for the next group.
+            // above passed): the other im2col buffer is free for the next group.  The helper learns it at this barrier.
+            named_bar_sync(1 + g, 64);
             if (j + stride < P.n_groups) {
                 build_group(buf ^ 1);
                 if (j + 2 * stride < P.n_groups) load_group(j + 2 * stride);
             }
-            for (uint32_t tau = 1; tau < T; tau++) issue_tile(buf, tau);
+            if (!helper) for (uint32_t tau = 1; tau < T; tau++) issue_tile(buf, tau);
         }
     } else {
         // ======================= consumer warpgroup g: thread r = TMEM lane r =======================
@@ -307,44 +390,71 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
         const uint32_t tm = tmem_base + (((warp & 3) * 32) << 16) + g * 224;
         const uint32_t bf0 = smem_u32(&bar_full[g][0]), bf1 = smem_u32(&bar_full[g][1]);
         const uint32_t be0 = smem_u32(&bar_free[g][0]), be1 = smem_u32(&bar_free[g][1]);
+        const uint32_t bgrp = smem_u32(&bar_group[g]);
         const int *wc = reinterpret_cast<const int *>(base + P.off_wc);
         int *imax = reinterpret_cast<int *>(base + P.off_imax) + g * 24;   // [3][8]
         uint32_t parity = 0, gcount = 0;
         const size_t stride = (size_t)gridDim.x * 2;
-        for (size_t j = (size_t)blockIdx.x * 2 + g; j < P.n_groups; j += stride, gcount++) {
-            int4 *raw = reinterpret_cast<int4 *>(base + P.off_raw + (g * 2 + (gcount & 1)) * P.raw_buf_bytes);
-            int *imx = imax + (gcount % 3) * 8;
-            for (uint32_t tau = 0; tau < T; tau++, parity ^= 1) {
-                const uint32_t item = tau * 128 + r, il = item / C, ch = item - il * C;
-                CnnTailW W;
-                {
-                    const int4 *w4 = reinterpret_cast<const int4 *>(wc + ch * 16);
-                    const int4 q0 = w4[0], q1 = w4[1], q2 = w4[2], q3 = w4[3];
-                    W.w01[0] = q0.x; W.w01[1] = q0.y; W.w01[2] = q0.z; W.wva = q0.w;
-                    W.wvb = q1.x; W.wsa = q1.y; W.wsb = q1.z; W.k3[0] = q1.w;
-                    W.k3[1] = q2.x; W.k3[2] = q2.y; W.k3[3] = q2.z; W.k3[4] = q2.w;
-                    W.k3[5] = q3.x; W.k3[6] = q3.y; W.k3[7] = q3.z; W.k3[8] = q3.w;
-                }
-                int f[4] = {0, 0, 0, 0};
-                cnn_tile_tail(tm, bf0, bf1, be0, be1, parity, W, f, P.err);
-                raw[item] = make_int4(f[0], f[1], f[2], f[3]);
-                atomicMax(&imx[il], max(max(f[0], f[1]), max(f[2], f[3])));
-            }
-            named_bar_sync(1 + g, 128);   // the group's raw features and per-image maxima are complete
-            // ReLUNorm over the C*4 features of each image (dll.c:80): all features are >= 0 here
+        // ReLUNorm over the C*4 features of each image (dll.c:80) needs the maximum over ALL channels of the image, i.e. over other
+        // threads' results.  It runs one group late: a group's threads publish their maxima (shared-memory atomicMax) and ARRIVE on
+        // the warpgroup's mbarrier without waiting; the wait comes a whole group of work later, when the phase has long completed,
+        // and only then are the (thread-private) raw features of the previous group normalised and stored.  No warp ever idles
+        // at a barrier for its slower siblings.
+        const uint32_t il_one = r / C, ch_one = r - il_one * C;   // T == 1 (C divides 128): the thread's image slot and channel never change
+        auto normalise_group = [&](size_t jg, uint32_t gc) {
+            const int4 *raw = reinterpret_cast<const int4 *>(base + P.off_raw + (g * 2 + (gc & 1)) * P.raw_buf_bytes);
+            const int *imx = imax + (gc % 3) * 8;
             for (uint32_t it = 0; it < T; it++) {
-                const uint32_t item = it * 128 + r, il = item / C, ch = item - il * C;
-                const size_t img = j * G + il;
+                const uint32_t item = it * 128 + r, il = T == 1 ? il_one : item / C, ch = T == 1 ? ch_one : item - il * C;
+                const size_t img = jg * G + il;
                 const int m = imx[il];
-                const uint32_t shift = 32u - (uint32_t)__clz(m >> 7);   // bit length of max >> 7 (inference.c:41-47)
+                const uint32_t shift = 32u - (uint32_t)__clz(m >> 7);   // bit length of max >> 7 (inference.c:41-47); features are >= 0
                 const int rounding = (int)((1u << shift) >> 1);
                 const int4 v = raw[item];
                 const uint32_t packed = (uint32_t)min(127, (v.x + rounding) >> shift) | ((uint32_t)min(127, (v.y + rounding) >> shift) << 8) |
                                         ((uint32_t)min(127, (v.z + rounding) >> shift) << 16) | ((uint32_t)min(127, (v.w + rounding) >> shift) << 24);
                 if (img < P.n) *reinterpret_cast<uint32_t *>(P.feats + img * P.feat_stride + ch * 4) = packed;
             }
-            // the maxima buffer of the group after next (last read two groups ago, behind a barrier) is cleared here
-            if (r < 8) imax[((gcount + 2) % 3) * 8 + r] = 0;
+        };
+        CnnTailW W;
+        auto load_weights = [&](uint32_t ch) {
+            const int4 *w4 = reinterpret_cast<const int4 *>(wc + ch * 16);
+            const int4 q0 = w4[0], q1 = w4[1], q2 = w4[2], q3 = w4[3];
+            W.w01[0] = q0.x; W.w01[1] = q0.y; W.w01[2] = q0.z; W.wva = q0.w;
+            W.wvb = q1.x; W.wsa = q1.y; W.wsb = q1.z; W.k3[0] = q1.w;
+            W.k3[1] = q2.x; W.k3[2] = q2.y; W.k3[3] = q2.z; W.k3[4] = q2.w;
+            W.k3[5] = q3.x; W.k3[6] = q3.y; W.k3[7] = q3.z; W.k3[8] = q3.w;
+        };
+        load_weights(ch_one);
+        size_t j_prev = 0;
+        for (size_t j = (size_t)blockIdx.x * 2 + g; j < P.n_groups; j_prev = j, j += stride, gcount++) {
+            int4 *raw = reinterpret_cast<int4 *>(base + P.off_raw + (g * 2 + (gcount & 1)) * P.raw_buf_bytes);
+            for (uint32_t tau = 0; tau < T; tau++, parity ^= 1) {
+                const uint32_t item = tau * 128 + r;
+                if (T > 1) load_weights(item % C);   // T == 1: the thread's channel never changes, loaded once above
+                int f[4] = {0, 0, 0, 0};
+                cnn_tile_tail<kConv3Packed>(tm, bf0, bf1, be0, be1, parity, W, f, P.err);
+                raw[item] = make_int4(f[0], f[1], f[2], f[3]);   // thread-private slot: read back only by this thread
+            }
+            // end of group gcount: (1) finish the previous group, (2) clear the maxima of the next one, (3) publish ours, (4) arrive
+            if (gcount > 0) {
+                mbar_wait_a(bgrp, (gcount - 1) & 1, P.err, 14);
+                normalise_group(j_prev, gcount - 1);
+            }
+            if (r < 8) imax[((gcount + 1) % 3) * 8 + r] = 0;
+            {
+                int *imx = imax + (gcount % 3) * 8;
+                for (uint32_t it = 0; it < T; it++) {
+                    const uint32_t item = it * 128 + r;
+                    const int4 v = raw[item];
+                    atomicMax(&imx[T == 1 ? il_one : item / C], max(max(v.x, v.y), max(v.z, v.w)));
+                }
+            }
+            mbar_arrive_a(bgrp);
+        }
+        if (gcount > 0) {
+            mbar_wait_a(bgrp, (gcount - 1) & 1, P.err, 14);
+            normalise_group(j_prev, gcount - 1);
         }
     }
     tc_fence_before();
@@ -387,7 +497,7 @@ bool cnn_frontend_tc_supported(uint32_t channels, uint32_t xy) {
 // returns false when the shape is not covered (the caller then uses k_cnn_frontend16)
 bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
                             uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err,
-                            cudaStream_t st) {
+                            bool conv3_fits_u16, cudaStream_t st) {
     CnnTcParams p{};
     size_t smem = cnn_tc_plan(channels, xy, p);
     if (!smem) return false;
@@ -396,7 +506,8 @@ bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t
     p.n_groups = (n + p.G - 1) / p.G;
     static size_t granted = 0;
     if (smem > granted) {
-        if (cudaFuncSetAttribute(k_cnn_frontend16_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        if (cudaFuncSetAttribute(k_cnn_frontend16_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_cnn_frontend16_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();   // not sticky: leave no stale error behind for the caller's launch check
             return false;
         }
@@ -404,7 +515,8 @@ bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t
     }
     const size_t want = (p.n_groups + 1) / 2;
     const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sm_count);
-    k_cnn_frontend16_tc<<<grid, kCnnTcThreads, smem, st>>>(p);
+    if (conv3_fits_u16) k_cnn_frontend16_tc<true><<<grid, kCnnTcThreads, smem, st>>>(p);
+    else k_cnn_frontend16_tc<false><<<grid, kCnnTcThreads, smem, st>>>(p);
     return true;
 }
 

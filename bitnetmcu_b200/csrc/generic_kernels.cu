@@ -242,6 +242,107 @@ void launch_quantize_images(const float *in, uint32_t elems, int8_t *out, size_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Emulation mode: the normalisation rules of the reference's Python emulator QuantizedModel.inference_quantized
+// (/root/reference/BitNetMCU.py:420-535) instead of the C engine's -- SURVEY.md 8f rank 4.  The emulator works on weight LEVELS
+// (4bitsym +-0.5..+-7.5, 2bitsym +-0.5/+-1.5: half the engine's integer weights) in float64; every quantity below is an exact dyadic
+// rational, so the integer restatement reproduces it bit for bit:
+//   BitLinear (452-457): conv = acc / level_scale;  rescale = 2^floor(log2(127 / max(conv.max, 1e-5)));
+//                        out = round_half_even(conv * rescale).clip(0, 127)
+//   BitConv2d (495-499): out = round_half_even(relu(conv) * (127.0 / max over the image)).clip(0, 127)   (float64, as NumPy)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_relunorm_emul(const int32_t *__restrict__ in, uint32_t n_in, int level_shift, int8_t *__restrict__ out,
+                                                        uint32_t out_stride, size_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int32_t *x = in + row * n_in;
+    int32_t m = INT32_MIN;
+    for (uint32_t i = lane; i < n_in; i += 32) m = max(m, x[i]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    // k = floor(log2(127 * level_scale / m)): the largest k with m * 2^k <= 127 * level_scale (k < 0: m <= (127 * level_scale) << -k)
+    int e = 0;
+    if (m > 0) {
+        const long long t = 127ll << level_shift;
+        int k = 0;
+        if ((long long)m <= t) { while (((long long)m << (k + 1)) <= t) k++; }
+        else { k = -1; while ((long long)m > (t << -k)) k--; }
+        e = k - level_shift;   // out = round_half_even(acc * 2^e)
+    }
+    int8_t *y = out + row * out_stride;
+    for (uint32_t i = lane; i < out_stride; i += 32) {
+        int r = 0;
+        if (i < n_in && m > 0) {
+            const int32_t v = x[i];
+            if (v > 0) {
+                long long q;
+                if (e >= 0) q = (long long)v << e;
+                else {
+                    const int sft = -e;
+                    q = (long long)v >> sft;
+                    const long long rem = (long long)v & ((1ll << sft) - 1), half = 1ll << (sft - 1);
+                    if (rem > half || (rem == half && (q & 1))) q++;   // np.round: half to even
+                }
+                r = (int)(q > 127 ? 127 : q);
+            }
+        }
+        y[i] = (int8_t)r;
+    }
+}
+
+// images int8 [n][256] -> int32 planes [(image, channel)][256], the copy loop of dll.c:68-70 for every channel
+__global__ void k_expand_image(const int8_t *__restrict__ img, int32_t *__restrict__ planes, uint32_t C, uint32_t elems, size_t n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * C * elems) return;
+    const size_t item = idx / elems;
+    planes[idx] = img[(item / C) * elems + idx % elems];
+}
+
+// per image: v = round_half_even(v * (127.0 / max)).clip(0, 127) over its C * H * W conv outputs (already >= 0), float64 like NumPy
+__global__ void __launch_bounds__(256) k_conv_renorm(int32_t *__restrict__ planes, uint32_t elems, size_t n) {
+    __shared__ int s_max[8];
+    int32_t *p = planes + (size_t)blockIdx.x * elems;
+    int m = 0;
+    for (uint32_t i = threadIdx.x; i < elems; i += 256) m = max(m, p[i]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_max[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) m = max(m, s_max[w]);
+    if (m <= 0) return;   // all-zero conv output: NumPy divides by zero here (nan); defined as zeros
+    const double scale = 127.0 / (double)m;
+    for (uint32_t i = threadIdx.x; i < elems; i += 256) {
+        const double y = rint(__dmul_rn((double)p[i], scale));
+        p[i] = (int)fmin(fmax(y, 0.0), 127.0);
+    }
+}
+
+__global__ void k_i32_to_i8(const int32_t *__restrict__ in, uint32_t n_in, int8_t *__restrict__ out, uint32_t out_stride, size_t n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * out_stride) return;
+    const size_t row = idx / out_stride;
+    const uint32_t c = idx % out_stride;
+    out[idx] = c < n_in ? (int8_t)in[row * n_in + c] : (int8_t)0;
+}
+
+void launch_relunorm_emul(const int32_t *in, uint32_t n_in, int level_shift, int8_t *out, uint32_t out_stride, size_t n, cudaStream_t st) {
+    if (n) k_relunorm_emul<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(in, n_in, level_shift, out, out_stride, n);
+}
+void launch_expand_image(const int8_t *img, int32_t *planes, uint32_t C, uint32_t elems, size_t n, cudaStream_t st) {
+    const size_t total = n * C * elems;
+    if (total) k_expand_image<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, planes, C, elems, n);
+}
+void launch_conv_renorm(int32_t *planes, uint32_t elems_per_image, size_t n, cudaStream_t st) {
+    if (n && elems_per_image) k_conv_renorm<<<(unsigned)n, 256, 0, st>>>(planes, elems_per_image, n);
+}
+void launch_i32_to_i8(const int32_t *in, uint32_t n_in, int8_t *out, uint32_t out_stride, size_t n, cudaStream_t st) {
+    const size_t total = n * out_stride;
+    if (total) k_i32_to_i8<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, n_in, out, out_stride, n);
+}
+
+// ------------------------------------------------------------------------------------------------
 // processconv33ReLU / processmaxpool22, one thread per output element
 // ------------------------------------------------------------------------------------------------
 __global__ void k_conv33relu(const int32_t *__restrict__ act, const int8_t *__restrict__ w, uint32_t n_w, uint32_t xy,
@@ -417,12 +518,29 @@ __global__ void __launch_bounds__(kCnnThreads) k_cnn_frontend16(const int8_t *__
     }
 }
 
+// Static range of conv3's inputs for given HOST weights (int8 [C][9] each): conv1 sums are at most 127 * (sum of positive taps) +
+// 128 * (sum of |negative taps|) for int8 pixels, ReLU >> 4 of that bounds conv2's inputs (all >= 0), so only conv2's positive taps
+// raise its maximum; ReLU >> 4 again bounds the pooled values.  (per-channel static range proofs.)
+bool cnn_conv3_fits_u16(const int8_t *w1, const int8_t *w2, uint32_t channels) {
+    for (uint32_t c = 0; c < channels; c++) {
+        long long pos1 = 0, neg1 = 0, pos2 = 0;
+        for (int k = 0; k < 9; k++) {
+            const int a = w1[c * 9 + k], b = w2[c * 9 + k];
+            if (a > 0) pos1 += a; else neg1 -= a;
+            if (b > 0) pos2 += b;
+        }
+        const long long b1 = (127 * pos1 + 128 * neg1) >> 4;
+        if (((b1 * pos2) >> 4) > 65535) return false;
+    }
+    return true;
+}
+
 bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
                          uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int frontend, int *d_err,
-                         cudaStream_t st) {
+                         bool conv3_fits_u16, cudaStream_t st) {
     if (xy != 16 || channels == 0) return false;
     if (n == 0) return true;
-    if (frontend != 1 && launch_cnn_frontend_tc(images, w1, w2, w3, channels, xy, features, feat_stride, n, sm_count, d_err, st)) return true;
+    if (frontend != 1 && launch_cnn_frontend_tc(images, w1, w2, w3, channels, xy, features, feat_stride, n, sm_count, d_err, conv3_fits_u16, st)) return true;
     if (frontend == 2 || channels > kCnnThreads) return false;
     uint32_t ipb = kCnnThreads / channels;
     size_t smem = (size_t)ipb * (64 + 224) * 4 + ipb * 4;

@@ -50,14 +50,23 @@ void launch_maxpool22(const int32_t *act, uint32_t xy, int32_t *out, size_t n, c
 // frontend: 0 = tensor-core kernel when the shape is covered, else CUDA cores; 1 = CUDA cores (k_cnn_frontend16); 2 = tensor cores only
 bool launch_cnn_frontend(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
                          uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int frontend, int *d_err,
-                         cudaStream_t st);
+                         bool conv3_fits_u16, cudaStream_t st);
+// conv3_fits_u16: the pooled conv2 outputs (conv3's inputs) cannot exceed 65535 for this model's conv1 / conv2 weights
+// (cnn_conv3_fits_u16, computed once per model): conv3 may then run on IDP.2A
+bool cnn_conv3_fits_u16(const int8_t *w1, const int8_t *w2, uint32_t channels);
 bool cnn_frontend_tc_supported(uint32_t channels, uint32_t xy);
 
 // same front-end with conv1 on tcgen05 and the depthwise tail fed from TMEM (cnn_tcgen05.cu); false when the shape is not
 // covered (channels not a multiple of 16, > 128, or geometry other than 16x16)
 bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t *w2, const int8_t *w3, uint32_t channels,
                             uint32_t xy, int8_t *features, uint32_t feat_stride, size_t n, int sm_count, int *d_err,
-                            cudaStream_t st);
+                            bool conv3_fits_u16, cudaStream_t st);
+
+// emulation mode (BitNetMCU.py:420-535): normalisation rules of the reference's Python emulator, see generic_kernels.cu
+void launch_relunorm_emul(const int32_t *in, uint32_t n_in, int level_shift, int8_t *out, uint32_t out_stride, size_t n, cudaStream_t st);
+void launch_expand_image(const int8_t *img, int32_t *planes, uint32_t C, uint32_t elems, size_t n, cudaStream_t st);
+void launch_conv_renorm(int32_t *planes, uint32_t elems_per_image, size_t n, cudaStream_t st);
+void launch_i32_to_i8(const int32_t *in, uint32_t n_in, int8_t *out, uint32_t out_stride, size_t n, cudaStream_t st);
 
 // input quantisation ahead of the path (test_inference.py:140-141): float [n][elems] -> int8 [n][elems]
 void launch_quantize_images(const float *in, uint32_t elems, int8_t *out, size_t n, cudaStream_t st);

@@ -55,6 +55,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
     }
 }
 
+// Long waits of a helper warp that shares its SM sub-partition with working warps (producer / issuer roles): every failed probe is
+// followed by a sleep, so the waiting warp takes (almost) no issue slots from its neighbours.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, int *err_flag = nullptr, int code = 1, uint32_t sleep_ns = 400) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        __nanosleep(sleep_ns);
+        if (++spins > (1u << 22)) {
+            if (err_flag) atomicExch(err_flag, code);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+
 // same, on a 32-bit shared-memory address held in a register (hot loops: no generic->shared conversion per call)
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
     uint32_t ok;

@@ -104,6 +104,15 @@ class Engine:
                                                    lab_ptr, C.c_void_p(stream)), "bnm_infer_batch_device")
 
 
+    def inference_quantized(self, input_data: np.ndarray) -> np.ndarray:
+        """``QuantizedModel.inference_quantized`` (/root/reference/BitNetMCU.py:420-535) on the GPU: float32 images [n, img_bytes]
+        -> float64 logits [n, n_classes] with the Python emulator's normalisation rules (not the C engine's): what
+        ``np.argmax`` is taken of in test_inference.py:153-154 and exportquant.py:537-559."""
+        x = np.ascontiguousarray(input_data, dtype=np.float32).reshape(-1, self.img_bytes)
+        out = np.empty((x.shape[0], self.n_classes), dtype=np.float64)
+        _lib.check(self.lib.bnm_emulate_inference_quantized(self.handle, _ptr(x), x.shape[0], _ptr(out)), "bnm_emulate_inference_quantized")
+        return out
+
     def infer_tensor(self, images):
         """images: torch.int8 [n, img_bytes] on this engine's GPU -> (logits torch.int32 [n, n_classes], labels torch.int32 [n]) on
         the same GPU, asynchronous on torch's current stream (device memory end to end; plumbing for ``dist.sharded_infer``)."""

@@ -194,6 +194,17 @@ BNM_API int bnm_maxpool22_batch(const int32_t *activations, uint32_t xy_input, i
 BNM_API int bnm_quantize_images(const float *images, size_t n, uint32_t elems, int8_t *out);                       /* host buffers */
 BNM_API int bnm_quantize_images_device(const float *images, size_t n, uint32_t elems, int8_t *out, void *stream);  /* device buffers */
 
+/* ---------------------------------------------------------------------------------------------
+ * 6. Emulation mode: QuantizedModel.inference_quantized of the reference on the GPU
+ *    (/root/reference/BitNetMCU.py:420-535; what exportquant.py:537-559 and test_inference.py:153-154 call per image).
+ *    images float32 [n][img_bytes] (host) -> float64 [n][n_classes] (host): the emulator's logits, i.e. WITH its normalisation
+ *    rules (rescale = 2^floor(log2(127/max)), np.round; per-image conv renormalisation), which differ from the C engine's by
+ *    design.  Exact for Binary / Ternary / 2bitsym / 4bitsym / 8bit / FP130 weights; the reference's
+ *    "4bit" levels carry a +0.01 offset (BitNetMCU.py:159) and NF4 levels are non-dyadic: those two are approximated by the
+ *    engine's integer weights (statistical parity only).
+ * ------------------------------------------------------------------------------------------- */
+BNM_API int bnm_emulate_inference_quantized(bnm_model *m, const float *images, size_t n, double *logits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -548,3 +548,22 @@ def test_cnn_frontends_agree_for_every_channel_count(lib, oracle, channels):
             lo, la = e.infer(imgs)
             assert np.array_equal(lo, want) and np.array_equal(la, want_lab), (channels, n, fe, np.argwhere(lo != want)[:4])
             e.close()
+
+
+# ---- emulation mode: QuantizedModel.inference_quantized on the GPU -----------------------------
+
+@pytest.mark.parametrize("name", ["fc", "1k", "12k_FP130", "2bitsym96", "8bit64", "binary160", "ternary64", "cnn", "cnn_48", "cnn_16small"])
+def test_inference_quantized_emulation_matches_reference_python(lib, name):
+    """tests/golden/emulator.npz holds the logits of the reference's own Python emulator (BitNetMCU.py:420-535, run in the build
+    container by tests/golden/make_emulator_golden.py) on 64 float32 images.  Every intermediate of the emulator is an exact
+    dyadic rational for these encodings (and the conv renormalisation is one IEEE float64 multiply + rint), so the GPU restatement
+    must reproduce the float64 logits exactly: tolerance 0."""
+    from bitnetmcu_b200.engine import Engine
+    g = np.load(os.path.join(GOLDEN, "emulator.npz"))
+    e = Engine(load_model(name))
+    got = e.inference_quantized(g["images"])
+    want = g[name]
+    assert got.shape == want.shape and got.dtype == np.float64
+    assert np.array_equal(got, want), (name, np.argwhere(got != want)[:5], got[0][:4], want[0][:4])
+    assert np.array_equal(np.argmax(got, axis=1), np.argmax(want, axis=1))
+    e.close()
