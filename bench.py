@@ -265,6 +265,34 @@ def log(*a):
 # ------------------------------------------------------------------------------------------------------------------
 # measurement helpers (GPU arm)
 # ------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and therefore its first-touch pinned allocations) to the CPUs of the NUMA node its GPU hangs off
+    (GPU0-3 <-> node 0, GPU4-7 <-> node 1 on these boxes): the e2e arm streams 268 MB per step through pinned host memory, and a
+    rank running on the far socket pays the inter-socket hop on every byte.  Best effort; returns a short description."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        if bus is None:
+            return "pci bus id unavailable"
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(path + "/numa_node").read().strip())
+        cpulist = open(path + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if node < 0 or not cpus:
+            return f"numa_node {node}: not bound"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to NUMA node {node} ({len(cpus)} CPUs)"
+    except Exception as ex:
+        return f"not bound: {ex}"
+
+
 class Ctx:
     """torch plumbing shared by the measurements of one process / rank."""
 
@@ -278,6 +306,7 @@ class Ctx:
             os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's INFO log: stderr, not stdout (see claim_stdout)
             bdist.init_process_group("nccl")
         torch.cuda.set_device(self.local_rank)
+        self.numa = bind_to_gpu_numa_node(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         self.stream = torch.cuda.current_stream(self.dev)
 
@@ -337,6 +366,17 @@ def int_alu_peak_ops(sm_max_mhz):
     return 148 * 64 * 8 * sm_max_mhz * 1e6
 
 
+def epilogue_alu_bound(model, sm_max_mhz):
+    """Second ceiling of the fused FC kernel: the integer ALU pipe of the in-TMEM ReLUNorm.  Every hidden-layer accumulator costs
+    2.33 ALU-pipe instructions (VIADDMNMX.RELU + 1/2 VIMNMX3 + 3/4 PRMT; the shift is an IMAD on the FMA pipe) at one warp
+    instruction per 2 cycles per SM sub-partition (tools/alu_rates.cu): images/s <= 148 SMs x 4 x 32 lanes / (accumulators x 2.33 x 2
+    cycles) x clock.  Wide models (Binary-160: 480 hidden accumulators per image) hit this ceiling far below the HBM roofline."""
+    fc = model.fc_layers
+    acc = sum(l.n_out for l in fc[:-1])
+    ips = 148 * 4 * 32 / (max(acc, 1) * 2.33 * 2) * sm_max_mhz * 1e6
+    return {"hidden_accumulators_per_image": acc, "images_per_s": ips, "alu_instructions_per_accumulator": 2.33}
+
+
 def run_config(ctx, name, batch, steps, warmup, args, check_parity=True, host_imgs=None):
     """One BASELINE config: device-timed plain launches, its roofline, full-batch parity against the oracle (rank 0)."""
     from bitnetmcu_b200 import _lib
@@ -362,12 +402,19 @@ def run_config(ctx, name, batch, steps, warmup, args, check_parity=True, host_im
                 "macs_per_image": model.macs_per_image, "hbm_frac": hbm_ach / peak_gbs, "traffic": None}
     else:
         roof = {"bound": "hbm", "achieved": hbm_ach, "peak": peak_gbs, "unit": "GB/s", "frac": hbm_ach / peak_gbs,
-                "peak_source": peak_src, "algorithmic_bytes_per_image": bytes_per_image, "traffic": traffic_for(name, n)}
+                "peak_source": peak_src, "algorithmic_bytes_per_image": bytes_per_image, "traffic": traffic_for(name, n),
+                "alu_pipe_bound": epilogue_alu_bound(model, sm_max)}
+        roof["alu_pipe_bound"]["frac"] = value / ctx.world / roof["alu_pipe_bound"]["images_per_s"]
     out = {"name": name, "workload": workload_name(name, model, n), "value": value, "unit": UNIT, "ms_per_step": ms, "steps": steps,
            "warmup": warmup, "gpu_launches_per_step": eng.launch_count(n), "launch_semantics": "plain launches",
            "path": "tcgen05" if eng.active_path == _lib.PATH_TCGEN05 else "layers", "roofline": roof}
     if cnn:
         out["cnn_frontend"] = {0: "auto (tensor cores when covered)", 1: "CUDA cores", 2: "tensor cores"}.get(int(eng.lib.bnm_model_get_option(eng.handle, _lib.OPT_CNN_FRONTEND)))
+    if cnn:   # e2e through the C ABI with pinned host buffers for the CNN config too (three-stream chunk pipeline, per-slot feature buffers)
+        try:
+            out["e2e"] = e2e_through_c_abi(ctx, eng, host_imgs, steps=3, warm=2)
+        except Exception as ex:
+            out["e2e"] = {"error": str(ex)[:200]}
     if check_parity and ctx.rank == 0:
         try:
             from oracle.oracle import Oracle
@@ -385,6 +432,36 @@ def run_config(ctx, name, batch, steps, warmup, args, check_parity=True, host_im
     del db
     ctx.torch.cuda.empty_cache()
     return out
+
+
+def e2e_through_c_abi(ctx, eng, host_imgs, steps, warm=3, keep=None):
+    """The metric end to end through bnm_infer_batch: pinned host buffers in, pinned host buffers out, H2D + kernels + D2H inside the
+    timed region (wall clock around `steps` calls, max over ranks).  keep: dict that receives the result arrays of the last call."""
+    from bitnetmcu_b200 import _lib
+    lib = _lib.load()
+    n, C = host_imgs.shape[0], eng.n_classes
+    nb_in, nb_log, nb_lab = n * eng.img_bytes, n * C * 4, n * 4
+    p_in, p_log, p_lab = lib.bnm_host_alloc(nb_in), lib.bnm_host_alloc(nb_log), lib.bnm_host_alloc(nb_lab)
+    try:
+        h_in = np.ctypeslib.as_array((Ct.c_int8 * nb_in).from_address(p_in)).reshape(n, eng.img_bytes)
+        h_log = np.ctypeslib.as_array((Ct.c_int32 * (n * C)).from_address(p_log)).reshape(n, C)
+        h_lab = np.ctypeslib.as_array((Ct.c_uint32 * n).from_address(p_lab))
+        h_in[:] = host_imgs
+        eng.set_option(_lib.OPT_CHUNK_IMAGES, 1 << 17)
+        for _ in range(warm):
+            eng.infer(h_in, out_logits=h_log, out_labels=h_lab)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eng.infer(h_in, out_logits=h_log, out_labels=h_lab)
+        ctx.torch.cuda.synchronize()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        if keep is not None:
+            keep["logits"], keep["labels"] = h_log.copy(), h_lab.copy()
+        return {"value": ctx.world * n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": nb_in, "d2h_bytes_per_step": nb_log + nb_lab,
+                "ms_per_step": 1e3 * dt / steps, "api": "bnm_infer_batch (pinned host buffers, 3-stream chunk pipeline)"}
+    finally:
+        lib.bnm_host_free(p_in); lib.bnm_host_free(p_log); lib.bnm_host_free(p_lab)
 
 
 _TRAFFIC = None
@@ -542,24 +619,9 @@ def main():
     parity = None
     e2e = None
     if not args.no_e2e:
-        lib = _lib.load()
-        nb_in, nb_log, nb_lab = n * eng.img_bytes, n * C * 4, n * 4
-        p_in, p_log, p_lab = lib.bnm_host_alloc(nb_in), lib.bnm_host_alloc(nb_log), lib.bnm_host_alloc(nb_lab)
-        h_in = np.ctypeslib.as_array((Ct.c_int8 * nb_in).from_address(p_in)).reshape(n, eng.img_bytes)
-        h_log = np.ctypeslib.as_array((Ct.c_int32 * (n * C)).from_address(p_log)).reshape(n, C)
-        h_lab = np.ctypeslib.as_array((Ct.c_uint32 * n).from_address(p_lab))
-        h_in[:] = host_imgs
-        eng.set_option(_lib.OPT_CHUNK_IMAGES, 1 << 17)
-        for _ in range(3):
-            eng.infer(h_in, out_logits=h_log, out_labels=h_lab)
-        ctx.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.infer(h_in, out_logits=h_log, out_labels=h_lab)
-        torch.cuda.synchronize()
-        dt = ctx.max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": nb_in, "d2h_bytes_per_step": nb_log + nb_lab,
-               "ms_per_step": 1e3 * dt / args.steps, "api": "bnm_infer_batch (pinned host buffers, 3-stream chunk pipeline)"}
+        keep = {}
+        e2e = e2e_through_c_abi(ctx, eng, host_imgs, steps=args.steps, warm=3, keep=keep)
+        h_log, h_lab = keep["logits"], keep["labels"]
         try:
             from oracle.oracle import Oracle
             ns = min(n, 1 << 16)
@@ -572,7 +634,6 @@ def main():
                                          and np.array_equal(snap[1][0], h_log[::-1]) and np.array_equal(snap[1][1], h_lab[::-1]))
         except Exception as ex:  # the checker being unavailable must not hide the measurement
             parity = f"oracle unavailable: {ex}"
-        lib.bnm_host_free(p_in); lib.bnm_host_free(p_log); lib.bnm_host_free(p_lab)
 
     # ---- N > 1: the result exchange, timed separately -- `value` keeps the logits sharded
     gather = None
@@ -622,7 +683,8 @@ def main():
                        "parallelism": f"dp{world} (batch sharded, logits stay sharded; no data-path collective)",
                        "l2": "inputs larger than L2: two 268 MB image buffers alternated per step, TMA evict-first loads",
                        "path": "tcgen05" if eng.active_path == _lib.PATH_TCGEN05 else "layers",
-                       "launch_semantics": "plain launches (BNM_OPT_LAUNCH_OVERLAP = 0): ordinary stream semantics"},
+                       "launch_semantics": "plain launches (BNM_OPT_LAUNCH_OVERLAP = 0): ordinary stream semantics",
+                       "host_numa": ctx.numa},
             "value_overlapped_launches": world * n / (ms_overlap * 1e-3),
             "value_sustained": sustained,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,

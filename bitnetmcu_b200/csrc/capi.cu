@@ -51,6 +51,7 @@ struct PipeSlot {
     int8_t *d_images = nullptr;
     int32_t *d_logits = nullptr;
     uint32_t *d_labels = nullptr;
+    int8_t *d_feat = nullptr;    // CNN models: this slot's own feature buffer, so that the slots' chunks may overlap in time
 };
 
 struct bnm_model {
@@ -164,18 +165,21 @@ static int build_fc_dev(bnm_model *m) {
     return 0;
 }
 
-static int ensure_scratch(bnm_model *m, size_t n) {
-    if (n <= m->scratch_n) return 0;
+static int ensure_scratch(bnm_model *m, size_t n, bool layered) {
+    if (n <= m->scratch_n && (!layered || m->d_acc)) return 0;
+    n = std::max(n, m->scratch_n);
     cudaFree(m->d_acc);
     cudaFree(m->d_act[0]);
     cudaFree(m->d_act[1]);
     cudaFree(m->d_feat);
     m->d_acc = nullptr; m->d_act[0] = m->d_act[1] = nullptr; m->d_feat = nullptr;
     m->scratch_n = 0;
-    CU_TRY(cudaMalloc(&m->d_acc, n * (size_t)std::max(m->max_nout, 1u) * sizeof(int32_t)));
-    for (int i = 0; i < 2; i++) {
-        CU_TRY(cudaMalloc(&m->d_act[i], n * (size_t)m->max_kpad));
-        CU_TRY(cudaMemset(m->d_act[i], 0, n * (size_t)m->max_kpad));
+    if (layered) {   // int32 accumulators + ping-pong int8 activations of the layer-by-layer path; the fused path needs neither
+        CU_TRY(cudaMalloc(&m->d_acc, n * (size_t)std::max(m->max_nout, 1u) * sizeof(int32_t)));
+        for (int i = 0; i < 2; i++) {
+            CU_TRY(cudaMalloc(&m->d_act[i], n * (size_t)m->max_kpad));
+            CU_TRY(cudaMemset(m->d_act[i], 0, n * (size_t)m->max_kpad));
+        }
     }
     if (m->model_class == BNM_MODEL_CNNMNIST) {
         CU_TRY(cudaMalloc(&m->d_feat, n * (size_t)m->feat_stride));
@@ -316,6 +320,7 @@ extern "C" void bnm_model_destroy(bnm_model *m) {
         cudaFree(s.d_images);
         cudaFree(s.d_logits);
         cudaFree(s.d_labels);
+        cudaFree(s.d_feat);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     delete m;
@@ -379,6 +384,7 @@ extern "C" int64_t bnm_model_get_option(const bnm_model *m, int option) {
 // batched inference, device pointers
 // -----------------------------------------------------------------------------------------------
 static const size_t kLayeredChunk = 1 << 17;   // images per pass of the layer-by-layer path (bounds its scratch)
+static const size_t kFusedCnnChunk = 1 << 20;  // fused path, CNN models: images per front-end + FC launch pair (256 B of features each)
 
 // FC chain, one CUDA-core kernel per layer: input int8 [n][in_stride]
 static int run_fc_layers(bnm_model *m, const int8_t *in, uint32_t in_stride, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st) {
@@ -403,9 +409,9 @@ static int run_fc_layers(bnm_model *m, const int8_t *in, uint32_t in_stride, siz
     return 0;
 }
 
-// CNN front-end into m->d_feat (int8 [n][feat_stride])
-static int run_cnn_front(bnm_model *m, const int8_t *images, size_t n, cudaStream_t st) {
-    if (launch_cnn_frontend(images, m->d_conv[0], m->d_conv[1], m->d_conv[2], m->channels, m->xy0, m->d_feat, m->feat_stride, n,
+// CNN front-end into feat (int8 [n][feat_stride])
+static int run_cnn_front(bnm_model *m, const int8_t *images, size_t n, int8_t *feat, cudaStream_t st) {
+    if (launch_cnn_frontend(images, m->d_conv[0], m->d_conv[1], m->d_conv[2], m->channels, m->xy0, feat, m->feat_stride, n,
                             m->sm_count, m->cnn_frontend, m->d_err, m->conv3_fits_u16, st))
         return 0;
     return fail(BNM_E_UNSUPPORTED, "CNN front-end: %u channels at %ux%u not supported by the selected kernel (the reference hard-codes 16x16, dll.c:68)",
@@ -417,13 +423,16 @@ extern "C" int bnm_infer_launch_count(const bnm_model *m, size_t n) {
     const bool fused = bnm_model_active_path(m) == BNM_PATH_TCGEN05;
     const bool cnn = m->model_class == BNM_MODEL_CNNMNIST;
     if (fused && !cnn) return 1;
-    size_t chunks = (n + kLayeredChunk - 1) / kLayeredChunk;
+    const size_t chunk_images = fused ? kFusedCnnChunk : kLayeredChunk;
+    size_t chunks = (n + chunk_images - 1) / chunk_images;
     int per = cnn ? 1 : 0;
     per += fused ? 1 : (int)(2 * m->fc.size());   // fc + relunorm per layer (last relunorm = labels)
     return (int)(chunks * per);
 }
 
-static int infer_device_impl(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels, const GatherDst *gather, void *stream) {
+// slot_feat: a caller-owned feature buffer for n images (the host pipeline's per-slot buffers); null = the model's own scratch
+static int infer_device_impl(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels, const GatherDst *gather, void *stream,
+                             int8_t *slot_feat = nullptr) {
     if (!m || (n && (!images || !logits))) return fail(BNM_E_ARG, "bnm_infer_batch_device: null argument");
     if (n == 0) return 0;
     if (((uintptr_t)images | (uintptr_t)logits) & 15) return fail(BNM_E_ARG, "device buffers must be 16-byte aligned");
@@ -436,9 +445,10 @@ static int infer_device_impl(bnm_model *m, const int8_t *images, size_t n, int32
         int rc = fc_chain_launch(m->plan, images, n, logits, labels, gather, st);
         return rc ? fail(BNM_E_CUDA, "fused FC kernel launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())) : 0;
     }
-    const size_t chunk = std::min(n, kLayeredChunk);
-    int rc = ensure_scratch(m, chunk);
+    const size_t chunk = slot_feat ? n : std::min(n, fused ? kFusedCnnChunk : kLayeredChunk);
+    int rc = (slot_feat && fused) ? 0 : ensure_scratch(m, chunk, !fused);
     if (rc) return rc;
+    int8_t *feat = slot_feat ? slot_feat : m->d_feat;
     for (size_t b = 0; b < n; b += chunk) {
         const size_t nb = std::min(chunk, n - b);
         const int8_t *img = images + b * m->img_bytes;
@@ -447,9 +457,9 @@ static int infer_device_impl(bnm_model *m, const int8_t *images, size_t n, int32
         const int8_t *fc_in = img;
         uint32_t fc_stride = m->img_bytes;
         if (cnn) {
-            rc = run_cnn_front(m, img, nb, st);
+            rc = run_cnn_front(m, img, nb, feat, st);
             if (rc) return rc;
-            fc_in = m->d_feat;
+            fc_in = feat;
             fc_stride = m->feat_stride;
         }
         if (fused) {
@@ -571,22 +581,27 @@ extern "C" int bnm_infer_batch(bnm_model *m, const int8_t *images, size_t n, int
     if (m->slot_n < chunk) {
         CU_TRY(cudaDeviceSynchronize());
         for (auto &s : m->slots) {
-            cudaFree(s.d_images); cudaFree(s.d_logits); cudaFree(s.d_labels);
-            s.d_images = nullptr; s.d_logits = nullptr; s.d_labels = nullptr;
+            cudaFree(s.d_images); cudaFree(s.d_logits); cudaFree(s.d_labels); cudaFree(s.d_feat);
+            s.d_images = nullptr; s.d_logits = nullptr; s.d_labels = nullptr; s.d_feat = nullptr;
+            if (m->model_class == BNM_MODEL_CNNMNIST) {
+                CU_TRY(cudaMalloc(&s.d_feat, chunk * (size_t)m->feat_stride));
+                CU_TRY(cudaMemset(s.d_feat, 0, chunk * (size_t)m->feat_stride));
+            }
             CU_TRY(cudaMalloc(&s.d_images, chunk * (size_t)m->img_bytes));
             CU_TRY(cudaMalloc(&s.d_logits, chunk * (size_t)m->n_classes * sizeof(int32_t)));
             CU_TRY(cudaMalloc(&s.d_labels, chunk * sizeof(uint32_t)));
         }
         m->slot_n = chunk;
     }
-    // the layered / CNN paths share one scratch arena: their chunks must not overlap in time -> one stream
-    const bool shared_scratch = !(bnm_model_active_path(m) == BNM_PATH_TCGEN05 && m->model_class == BNM_MODEL_FCMNIST);
+    // the layer-by-layer path shares one scratch arena (accumulators / activations): its chunks must not overlap in time -> one
+    // stream.  The fused path has no shared state (CNN models: one feature buffer per slot) and uses all three.
+    const bool shared_scratch = bnm_model_active_path(m) != BNM_PATH_TCGEN05;
     size_t k = 0;
     for (size_t b = 0; b < n; b += chunk, k++) {
         const size_t nb = std::min(chunk, n - b);
         PipeSlot &s = m->slots[shared_scratch ? 0 : k % 3];
         CU_TRY(cudaMemcpyAsync(s.d_images, images + b * m->img_bytes, nb * (size_t)m->img_bytes, cudaMemcpyHostToDevice, s.stream));
-        int rc = bnm_infer_batch_device(m, s.d_images, nb, s.d_logits, labels ? s.d_labels : nullptr, s.stream);
+        int rc = infer_device_impl(m, s.d_images, nb, s.d_logits, labels ? s.d_labels : nullptr, nullptr, s.stream, shared_scratch ? nullptr : s.d_feat);
         if (rc) return rc;
         CU_TRY(cudaMemcpyAsync(logits + b * m->n_classes, s.d_logits, nb * (size_t)m->n_classes * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         if (labels) CU_TRY(cudaMemcpyAsync(labels + b, s.d_labels, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));

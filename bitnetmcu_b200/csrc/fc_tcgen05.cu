@@ -60,10 +60,7 @@ struct ChainParams {
     uint32_t *lab_dst[kMaxGatherDst];
     int32_t *log_dst[kMaxGatherDst];
     size_t row0;
-    // wide models (fc_chain_split_kernel): both warpgroups work on the SAME tile, warpgroup `part` takes the accumulator columns
-    // [split_col[l] * part, ...) of layer l (a multiple of 16)
-    uint32_t n_split;
-    uint32_t split_col[kMaxFcLayers];
+    uint32_t off_gstage;              // gather launches: smem offset of the per-warp staging rows for the bulk peer stores (0: none)
 };
 
 struct FcChainPlan {
@@ -76,7 +73,10 @@ struct FcChainPlan {
     int sm_count = 0;
     int device = 0;
     int overlap = 0;                  // BNM_OPT_LAUNCH_OVERLAP: 0 plain launch, 1 dependent launch + wait, 2 independent launches
-    bool split = false;               // wide model: fc_chain_split_kernel (two warpgroups per tile)
+    // gather launches (fused result exchange) stage each warp's 32 logits rows in shared memory and push them to the peers with
+    // one bulk copy per destination (full NVLink packets instead of 8-byte scattered stores): their own ring depth and layout
+    uint32_t g_n_stages = 0, g_off_w = 0, g_off_gstage = 0;
+    size_t g_smem_bytes = 0;
     // launch-path state (nothing on the launch path reads the environment or re-encodes a known tensor map)
     struct TmapSlot { const void *ptr = nullptr; size_t n = 0; CUtensorMap map; };
     TmapSlot tmaps[4];                // tensor maps of the most recent (pointer, n) pairs: double/triple-buffered callers hit every time
@@ -453,8 +453,26 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                                     }
                                 };
                                 store_row(dst);
-                                if (kGather)
+                                if (kGather && !(P.off_gstage && full_tile))
                                     for (uint32_t d = 0; d < P.n_log_dst; d++) store_row(P.log_dst[d] + (P.row0 + img) * ncls);   // peers, over NVLink
+                            }
+                            if (kGather && P.off_gstage && full_tile && P.n_log_dst) {
+                                // peers: this warp's 32 rows are contiguous at every destination (32 x 4 ncls bytes).  Stage them in
+                                // shared memory and push them with ONE bulk copy per destination -- full NVLink packets instead of
+                                // 8-byte stores scattered at a 4 ncls stride.
+                                int32_t *stg = reinterpret_cast<int32_t *>(smem + P.off_gstage) + warp * 32 * ncls;
+#pragma unroll
+                                for (int j = 0; j < 16; j++)
+                                    if ((uint32_t)j < ncls) stg[lane * ncls + j] = (int)x[j];
+                                fence_proxy_async_smem();
+                                __syncwarp();
+                                if (elect_one()) {
+                                    const size_t row = P.row0 + (size_t)tile * kTileM + quarter * 32;
+                                    for (uint32_t d = 0; d < P.n_log_dst; d++) bulk_store_1d(P.log_dst[d] + row * ncls, stg, 128 * ncls);
+                                    bulk_commit();
+                                    bulk_wait_read<0>();   // the staging rows may be overwritten by this warp's next tile
+                                }
+                                __syncwarp();
                             }
                         } else {
                             int best = -INT32_MAX;
@@ -504,208 +522,6 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1025 + 2 * blockIdx.x] = (long long)gt;
         uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); P.trace[1400 + blockIdx.x] = smid;
     }
-    if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Wide models (a hidden layer wider than 64 outputs: Binary-160, 2bitsym-96, ...).
-//
-// Their accumulator rows do not fit the register budget of one thread in one pass, and their TMEM footprint (D + A columns per
-// tile) leaves room for only 2-4 tiles in flight, so fc_chain_kernel's "one warpgroup per tile, two passes over TMEM" leaves the
-// tensor pipe idle behind long epilogues.  Here BOTH epilogue warpgroups work on the SAME tile: warpgroup `part` owns one half of
-// the accumulator columns of every hidden layer (<= 96 columns: one pass, everything in registers), the two warps that share a
-// TMEM lane quarter exchange their partial row maxima through shared memory (one 64-thread named barrier), and each writes its
-// half of the next layer's int8 A operand back into TMEM.  Epilogue steps are half as long, tiles in flight stay the same, TMEM is
-// read once.  Tile slots: kSlots per CTA (2 or 4, bounded by the 512 TMEM columns); issuer warp j issues the MMAs of the slots
-// with q % 2 == j.  Same barriers and ring as fc_chain_kernel; bar_ready counts 256 arrivals.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kSplitMaxUnits = 6;   // 16-column units per warp and step: half of a layer of up to 192 outputs
-
-__device__ __forceinline__ void relunorm_split(uint32_t d_addr, uint32_t a_addr, uint32_t n_units, int *xchg_mine, const int *xchg_other,
-                                               uint32_t bar_id) {
-    uint32_t v[kSplitMaxUnits][16];
-#pragma unroll
-    for (int u = 0; u < kSplitMaxUnits; u++)
-        if ((uint32_t)u < n_units) tmem_ld_x16(d_addr + 16 * u, v[u]);
-    tmem_ld_wait();
-    int m = 0;
-#pragma unroll
-    for (int u = 0; u < kSplitMaxUnits; u++)
-        if ((uint32_t)u < n_units) m = max16(v[u], m);
-    *xchg_mine = m;                      // partial (relu'd) row maximum of this half
-    named_bar_sync(bar_id, 64);          // the two warps of this TMEM lane quarter
-    const NormCoef k = norm_coef(max(m, *xchg_other));
-#pragma unroll
-    for (int u = 0; u < kSplitMaxUnits; u++)
-        if ((uint32_t)u < n_units) {
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) w[q] = norm_pack4(v[u][4 * q], v[u][4 * q + 1], v[u][4 * q + 2], v[u][4 * q + 3], k);
-            tmem_st_x4(a_addr + 4 * u, w);
-        }
-    tmem_st_wait();
-}
-
-constexpr int kSplitMaxSlots = 4;
-
-template <int kSlots, bool kGather>
-__global__ void __launch_bounds__(320, 1)
-fc_chain_split_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[2][kMaxStages], bar_mma[kSplitMaxSlots], bar_ready[kSplitMaxSlots];
-    __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(8) uint64_t bar_w;
-    __shared__ int s_xchg[2][2][128];   // [step parity][part][thread of the warpgroup]: partial row maxima
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    if (P.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const uint32_t n_st = P.n_stages;
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
-    const uint32_t my_tiles = tile0 < P.n_tiles ? (P.n_tiles - tile0 + tile_step - 1) / tile_step : 0;
-    const uint32_t n_rounds = (my_tiles + kSlots - 1) / kSlots;
-    const uint32_t w_base = smem_base + P.off_w;
-    const uint64_t l2_policy = policy_evict_first();
-    auto issue_tile_load = [&](uint32_t i) {
-        const uint32_t s = i % n_st;
-        uint64_t *bar = &bar_full[(i / n_st) & 1][s];
-        mbar_arrive_expect_tx(bar, P.stage_bytes);
-        const int32_t row = (int32_t)((tile0 + i * tile_step) * kTileM);
-        for (uint32_t a = 0; a < P.in_atoms; a++)
-            tma_load_2d_hint(smem + s * P.stage_bytes + a * 16384, &tmap_in, (int32_t)(a * 128), row, bar, l2_policy);
-    };
-
-    if (warp == 8) {
-        if (lane < 2 * kMaxStages) { if ((lane % kMaxStages) < n_st) mbar_init(&bar_full[lane / kMaxStages][lane % kMaxStages], 1); }
-        else if (lane < 2 * kMaxStages + kSplitMaxSlots) mbar_init(&bar_mma[lane - 2 * kMaxStages], 1);
-        else if (lane < 2 * kMaxStages + 2 * kSplitMaxSlots) mbar_init(&bar_ready[lane - 2 * kMaxStages - kSplitMaxSlots], 256);
-        else if (lane == 2 * kMaxStages + 2 * kSplitMaxSlots) mbar_init(&bar_w, 1);
-        fence_mbar_init();
-        __syncwarp();
-    }
-    if (tid == 256) {
-        mbar_arrive_expect_tx(&bar_w, P.w_bytes);
-        for (uint32_t off = 0; off < P.w_bytes; off += 32768)
-            bulk_load_1d(smem + P.off_w + off, P.w_image + off, min(32768u, P.w_bytes - off), &bar_w);
-        if (P.wait_prior_grid) asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
-    } else if (warp == 1) {
-        tmem_alloc<512>(&tmem_base_s);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-
-    if (warp >= 8) {
-        // ======================= MMA issuer warp j: slots q with q % 2 == j =======================
-        const uint32_t jw = warp - 8;
-        const bool leader = elect_one();
-        uint32_t ready_phase = 0;
-        mbar_wait(&bar_w, 0, P.err, 6);
-        for (uint32_t r = 0; r < n_rounds; r++)
-            for (int l = 0; l < P.n_layers; l++)
-#pragma unroll 1
-                for (int q = 0; q < kSlots; q++) {
-                    if (kSlots > 1 ? ((uint32_t)(q & 1) != jw) : (jw != 0)) continue;
-                    const uint32_t i = r * kSlots + q;
-                    if (i >= my_tiles) continue;
-                    const uint32_t d_tmem = tmem_base + q * P.tmem_wg_cols, a_tmem = d_tmem + P.tmem_a_off;
-                    if (r != 0 || l != 0) {
-                        mbar_wait(&bar_ready[q], (ready_phase >> q) & 1, P.err, 4);
-                        ready_phase ^= 1u << q;
-                    }
-                    if (l == 0) {
-                        const uint32_t s = i % n_st;
-                        mbar_wait(&bar_full[(i / n_st) & 1][s], (i / (2 * n_st)) & 1, P.err, 2);
-                        tc_fence_after();
-                        issue_layer1(P, smem_base + s * P.stage_bytes, w_base, d_tmem, leader);
-                    } else {
-                        tc_fence_after();
-                        issue_layer_ts(P, l, w_base, d_tmem, a_tmem, leader);
-                    }
-                    if (leader) umma_commit(&bar_mma[q]);
-                    __syncwarp();
-                }
-    } else {
-        // ======================= epilogue warps: warpgroup `part` takes its half of the columns =======================
-        const uint32_t part = warp >> 2, quarter = warp & 3;
-        const uint32_t lane_sel = (quarter * 32) << 16;
-        const uint32_t slot_cols = P.tmem_wg_cols, a_off = P.tmem_a_off;
-        const uint32_t bar_mma0 = smem_u32(&bar_mma[0]), bar_ready0 = smem_u32(&bar_ready[0]);
-        const int n_layers = P.n_layers;
-        const uint32_t tq = tid & 127;
-        uint32_t mma_phase = 0, step = 0;
-        for (uint32_t r = 0; r < n_rounds; r++)
-            for (int l = 0; l < n_layers; l++) {
-                const uint32_t n_pad_l = P.n_pad[l], h0 = P.split_col[l];
-                const uint32_t col0 = part ? h0 : 0, n_units = (part ? n_pad_l - h0 : h0) >> 4;
-#pragma unroll 1
-                for (int q = 0; q < kSlots; q++) {
-                    const uint32_t i = r * kSlots + q;
-                    if (i >= my_tiles) continue;
-                    const uint32_t d_tm = tmem_base + q * slot_cols + lane_sel;
-                    mbar_wait_a(bar_mma0 + q * 8, (mma_phase >> q) & 1, P.err, 3);
-                    mma_phase ^= 1u << q;
-                    tc_fence_after();
-                    if (l + 1 < n_layers) {
-                        if (l == 0 && part == 0 && quarter == 1 && i + n_st < my_tiles && elect_one()) issue_tile_load(i + n_st);   // stage is free
-                        relunorm_split(d_tm + col0, d_tm + a_off + (col0 >> 2), n_units, &s_xchg[step & 1][part][tq], &s_xchg[step & 1][part ^ 1][tq],
-                                       1 + quarter);
-                        step++;
-                        tc_fence_before();
-                        mbar_arrive_a(bar_ready0 + q * 8);
-                    } else if (kSlots > 1 ? part != (uint32_t)(q & 1) : part != 0) {
-                        // the other warpgroup writes this slot's logits (the two take alternate slots): nothing to read here
-                        mbar_arrive_a(bar_ready0 + q * 8);
-                    } else {
-                        // ---- logits + label, as in fc_chain_kernel (dll.c:115-116, inference.c:32-37)
-                        const uint32_t tile = tile0 + i * tile_step;
-                        const size_t img = (size_t)tile * kTileM + quarter * 32 + lane;
-                        const bool ok = (size_t)(tile + 1) * kTileM <= P.n || img < P.n;
-                        const uint32_t ncls = P.n_classes;
-                        int32_t *dst = P.logits + img * ncls;
-                        int best = -INT32_MAX;
-                        uint32_t pos = 255;
-                        for (uint32_t c = 0; c < ncls; c += 16) {
-                            uint32_t x[16];
-                            tmem_ld_x16(d_tm + c, x);
-                            tmem_ld_wait();
-                            int key = INT32_MIN;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                const int k0 = c + j < ncls ? (int)x[j] * 16 + (15 - j) : INT32_MIN;
-                                const int k1 = c + j + 1 < ncls ? (int)x[j + 1] * 16 + (14 - j) : INT32_MIN;
-                                key = __vimax3_s32(key, k0, k1);
-                            }
-                            const int cx = key >> 4;
-                            if (cx > best) { best = cx; pos = c + 15 - (key & 15); }
-                            if (ok) {
-#pragma unroll
-                                for (int j = 0; j < 16; j++)
-                                    if (c + j < ncls) dst[c + j] = (int)x[j];
-                                for (uint32_t d = 0; kGather && d < P.n_log_dst; d++) {
-                                    int32_t *pd = P.log_dst[d] + (P.row0 + img) * ncls;
-#pragma unroll
-                                    for (int j = 0; j < 16; j++)
-                                        if (c + j < ncls) pd[c + j] = (int)x[j];
-                                }
-                            }
-                        }
-                        tc_fence_before();
-                        mbar_arrive_a(bar_ready0 + q * 8);
-                        if (ok) {
-                            if (P.labels) P.labels[img] = pos;
-                            for (uint32_t d = 0; kGather && d < P.n_lab_dst; d++) P.lab_dst[d][P.row0 + img] = pos;
-                        }
-                    }
-                }
-            }
-    }
-    tc_fence_before();
-    __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
@@ -760,18 +576,7 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     p.tmem_a_off = round_up(d_cols, 32);
     p.tmem_wg_cols = p.tmem_a_off + round_up(std::max(a_cols, 1u), 16);
     if (p.tmem_wg_cols > 512) { delete plan; return fail("fused path: model does not fit the 512 TMEM columns"); }
-    uint32_t widest_hidden = 0;
-    for (int l = 0; l + 1 < n_layers; l++) widest_hidden = std::max(widest_hidden, layers[l].n_pad);
-    static const bool split_allowed = [] { const char *e = getenv("BNM_SPLIT"); return !e || atoi(e) != 0; }();   // A/B knob, read once per process
-    plan->split = split_allowed && n_layers >= 2 && widest_hidden > 64 && widest_hidden <= 16 * 2 * kSplitMaxUnits;
-    if (plan->split) {   // two warpgroups per tile (fc_chain_split_kernel), 1 / 2 / 4 tile slots
-        const uint32_t fit = 512 / p.tmem_wg_cols;
-        p.n_split = 2;
-        p.n_wg = 2;
-        p.n_slots = fit >= 4 ? 4 : (fit >= 2 ? 2 : 1);
-        if (const char *e = getenv("BNM_SLOTS")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && (uint32_t)v <= fit) p.n_slots = (uint32_t)v; }
-        for (int l = 0; l < n_layers; l++) p.split_col[l] = round_up(p.n_pad[l] / 2, 16);
-    } else {   // tiles in flight per CTA = n_wg warpgroups x n_slots slots, bounded by the 512 TMEM columns
+    {   // tiles in flight per CTA = n_wg warpgroups x n_slots slots, bounded by the 512 TMEM columns
         const uint32_t fit = 512 / p.tmem_wg_cols;
         p.n_wg = std::min<uint32_t>(kMaxWG, fit);
         p.n_slots = std::min<uint32_t>(kMaxSlots, fit / p.n_wg);
@@ -779,7 +584,7 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
         if (const char *e = getenv("BNM_WG")) p.n_wg = std::max(1, std::min<int>((int)p.n_wg, atoi(e)));          // tuning knobs
         if (const char *e = getenv("BNM_SLOTS")) p.n_slots = std::max(1, std::min<int>((int)std::min<uint32_t>(kMaxSlots, fit / p.n_wg), atoi(e)));
     }
-    const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 2560 /*static (the split kernel keeps 2.2 kB)*/;
+    const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*static*/;
     p.off_w = 0;  // set below: stages first (1024-aligned), then weights
     uint32_t fixed = round_up(p.w_bytes, 128);
     if (fixed + 2 * p.stage_bytes > smem_limit) { delete plan; return fail("fused path: weights do not fit in shared memory"); }
@@ -791,10 +596,20 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     // TMEM do not enforce it (launch_dependents fires before tmem_alloc blocks), shared memory does once a CTA asks for more than
     // half of the SM's 227 kB.
     plan->smem_bytes = std::max<size_t>(plan->smem_bytes, 116 * 1024);
+    if (p.n_classes <= 16) {   // staged peer stores: 12 warps x 32 rows x 4 n_classes bytes next to the weights
+        const uint32_t gstage = kMaxWG * 4 * 128 * p.n_classes;
+        const uint32_t fixed_g = round_up(p.w_bytes, 128) + round_up(gstage, 128);
+        if (fixed_g + 2 * p.stage_bytes <= smem_limit) {
+            plan->g_n_stages = std::min<uint32_t>(p.n_stages, (smem_limit - fixed_g) / p.stage_bytes);
+            plan->g_off_w = plan->g_n_stages * p.stage_bytes;
+            plan->g_off_gstage = plan->g_off_w + round_up(p.w_bytes, 128);
+            plan->g_smem_bytes = std::max<size_t>((size_t)plan->g_off_gstage + round_up(gstage, 128) + 1024, 116 * 1024);
+        }
+    }
     if (const char *e = getenv("BNM_TRACE")) plan->trace_path = e;                                   // diagnostics, read once
     if (const char *e = getenv("BNM_STAGGER_NS")) plan->stagger_override = (int)(atof(e) * 1.8);     // tuning knob; ~1.8 cycles per ns under load
     for (int j = 0; j < 16; j++) p.kadd[j] = (uint32_t)j < p.n_classes ? 15 - j : -(1 << 30);
-    plan->threads = p.n_wg * 160;   // 4 epilogue warps + 1 issuer warp per warpgroup (split kernel: 8 + 2 warps)
+    plan->threads = p.n_wg * 160;   // 4 epilogue warps + 1 issuer warp per warpgroup
     plan->in_bytes = in_bytes;
     plan->sm_count = sm_count;
     plan->device = device;
@@ -819,16 +634,10 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     p.err = plan->d_err;
     if (cudaFuncSetAttribute(fc_chain_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(plan->smem_bytes, plan->g_smem_bytes)) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(plan->smem_bytes, plan->g_smem_bytes)) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_split_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_split_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_split_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_split_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_split_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_split_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
+        cudaFuncSetAttribute(fc_chain_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
         return fail("cannot opt in to the required dynamic shared memory");
     }
@@ -889,6 +698,18 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
         for (uint32_t d = 0; d < p.n_lab_dst; d++) p.lab_dst[d] = gather->labels_dst[d];
         for (uint32_t d = 0; d < p.n_log_dst; d++) p.log_dst[d] = gather->logits_dst[d];
     }
+    size_t smem_bytes = plan->smem_bytes;
+    p.off_gstage = 0;
+    if (p.n_log_dst && plan->g_smem_bytes && (p.row0 * p.n_classes) % 4 == 0) {   // 16-byte aligned destination rows: staged bulk stores
+        bool aligned = true;
+        for (uint32_t d = 0; d < p.n_log_dst; d++) aligned = aligned && ((uintptr_t)p.log_dst[d] & 15) == 0;
+        if (aligned) {
+            p.n_stages = plan->g_n_stages;
+            p.off_w = plan->g_off_w;
+            p.off_gstage = plan->g_off_gstage;
+            smem_bytes = plan->g_smem_bytes;
+        }
+    }
     p.n_tiles = (uint32_t)((n + kTileM - 1) / kTileM);
     const CUtensorMap *tmap_p = plan_tensor_map(plan, in, n);
     if (!tmap_p) return -3;
@@ -907,7 +728,7 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     p.early_trigger = plan->overlap != 0 && grid == (unsigned)plan->sm_count;
     if (plan->stagger_override >= 0) p.stagger_cycles = (uint32_t)plan->stagger_override;
     plan->prev_in = in; plan->prev_logits = logits; plan->prev_labels = labels; plan->prev_stream = st; plan->prev_valid = true;
-    if (trace_path && !plan->split) {
+    if (trace_path) {
         if (p.n_slots == 1) fc_chain_kernel<1, true, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
         else fc_chain_kernel<2, true, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
     } else {
@@ -915,7 +736,7 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3((unsigned)plan->threads);
-        cfg.dynamicSmemBytes = plan->smem_bytes;
+        cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -923,16 +744,11 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
         cfg.attrs = attr;
         cfg.numAttrs = plan->overlap ? 1 : 0;
         const bool g = p.n_lab_dst || p.n_log_dst;
-        cudaError_t e;
-        if (plan->split)
-            e = p.n_slots == 4 ? (g ? cudaLaunchKernelEx(&cfg, fc_chain_split_kernel<4, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_split_kernel<4, false>, tmap, p))
-              : p.n_slots == 2 ? (g ? cudaLaunchKernelEx(&cfg, fc_chain_split_kernel<2, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_split_kernel<2, false>, tmap, p))
-                               : (g ? cudaLaunchKernelEx(&cfg, fc_chain_split_kernel<1, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_split_kernel<1, false>, tmap, p));
-        else e = p.n_slots == 1 ? (g ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, false>, tmap, p))
+        cudaError_t e = p.n_slots == 1 ? (g ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, false>, tmap, p))
                                        : (g ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<2, false, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_kernel<2, false, false>, tmap, p));
         if (e != cudaSuccess) return -4;
     }
-    if (trace_path && !plan->split) {   // diagnostics only: synchronous dump of the phase clocks
+    if (trace_path) {   // diagnostics only: synchronous dump of the phase clocks
         std::vector<long long> h(2048);
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), d_trace, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);

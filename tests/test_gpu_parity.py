@@ -567,3 +567,57 @@ def test_inference_quantized_emulation_matches_reference_python(lib, name):
     assert np.array_equal(got, want), (name, np.argwhere(got != want)[:5], got[0][:4], want[0][:4])
     assert np.array_equal(np.argmax(got, axis=1), np.argmax(want, axis=1))
     e.close()
+
+
+# ---- fused result exchange: the epilogue stores rows into other buffers as well ---------------------------------
+
+def _gather_case(lib, oracle, name, n, dst_device):
+    """One engine on GPU 0; destination buffers on `dst_device` (0: plain second buffers; 1: peer memory over NVLink)."""
+    import torch
+    from bitnetmcu_b200 import _lib
+    import ctypes as Ct
+    m = load_model(name)
+    imgs = _rand_images(n, seed=77)
+    want, want_lab = oracle.infer(m, imgs)
+    e = _engine(name, _lib.PATH_TCGEN05)
+    if dst_device != 0:
+        _lib.check(lib.bnm_enable_peer_access(0, dst_device), "bnm_enable_peer_access")
+    C_ = m.n_classes
+    rows, off = n + 640, 512            # destination holds more rows; this call's rows land at row_offset 512
+    dst_log = [torch.full((rows, C_), -7, dtype=torch.int32, device=f"cuda:{dst_device}") for _ in range(2)]
+    dst_lab = [torch.full((rows,), -7, dtype=torch.int32, device=f"cuda:{dst_device}") for _ in range(2)]
+    d_img = torch.from_numpy(imgs).cuda(0)
+    d_log = torch.empty((n, C_), dtype=torch.int32, device="cuda:0")
+    d_lab = torch.empty(n, dtype=torch.int32, device="cuda:0")
+    g = _lib.BnmGather()
+    g.n_labels_dst, g.n_logits_dst, g.row_offset = 2, 2, off
+    for k in range(2):
+        g.labels_dst[k] = dst_lab[k].data_ptr()
+        g.logits_dst[k] = dst_log[k].data_ptr()
+    torch.cuda.synchronize()
+    with torch.cuda.device(0):
+        s = torch.cuda.current_stream()
+        _lib.check(lib.bnm_infer_batch_device_gather(e.handle, Ct.c_void_p(d_img.data_ptr()), n, Ct.c_void_p(d_log.data_ptr()),
+                                                     Ct.c_void_p(d_lab.data_ptr()), Ct.byref(g), Ct.c_void_p(s.cuda_stream)), "gather")
+        s.synchronize()
+    assert np.array_equal(d_log.cpu().numpy(), want) and np.array_equal(d_lab.cpu().numpy().astype(np.uint32), want_lab)
+    for k in range(2):
+        gl, gb = dst_log[k].cpu().numpy(), dst_lab[k].cpu().numpy()
+        assert np.array_equal(gl[off:off + n], want), (name, n, dst_device, k)
+        assert np.array_equal(gb[off:off + n].astype(np.uint32), want_lab)
+        assert (gl[:off] == -7).all() and (gl[off + n:] == -7).all() and (gb[:off] == -7).all() and (gb[off + n:] == -7).all()   # nothing else touched
+    e.close()
+
+
+@pytest.mark.parametrize("name,n", [("fc", 148 * 128 * 2 + 77), ("fc", 1000), ("cnn_letters", 3000), ("binary160", 5000), ("cnn_48", 2049)])
+def test_fused_gather_epilogue_same_gpu(lib, oracle, name, n):
+    """bnm_infer_batch_device_gather with destinations on the same GPU: full tiles take the staged bulk-store path (16-byte
+    aligned rows), the ragged last tile and > 16 classes (cnn_letters: 37) the direct stores; rows outside the call stay untouched."""
+    _gather_case(lib, oracle, name, n, 0)
+
+
+def test_fused_gather_epilogue_peer_gpu(lib, oracle):
+    """Same with the destinations in the memory of a second GPU (P2P over NVLink), when the box has one."""
+    if lib.bnm_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _gather_case(lib, oracle, "fc", 148 * 128 * 3 + 5, 1)
