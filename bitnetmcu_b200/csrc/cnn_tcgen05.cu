@@ -39,9 +39,10 @@
 
 namespace bnm {
 
-constexpr uint32_t kCnnTcThreads = 384;          // 2 consumer warpgroups (8 warps) + 2 producer pairs (4 warps, one per SM sub-partition)
+constexpr uint32_t kCnnTcMaxThreads = 480;       // 3 consumer warpgroups (12 warps) + 3 producer / MMA-issuer warps
 constexpr uint32_t kPlaneBytes = 224 * 16;       // im2col plane of one image: 14 rows x 16 positions x 16 bytes
-constexpr uint32_t kHalfCols = 112;              // accumulator half: conv1 rows 0..6 / 7..13, 16 columns each
+constexpr uint32_t kPieceCols = 64;               // accumulator piece: four conv1 rows of 16 columns
+constexpr uint32_t kMaxCnnWG = 3;                 // consumer warpgroups: 3 x (2 buffers x 64 columns) = 384 of the 512 TMEM columns
 
 struct CnnTcParams {
     const int8_t *images;
@@ -57,9 +58,10 @@ struct CnnTcParams {
     uint32_t n_chunks_max;         // K-chunks (image slots) per tile, rounded up to even
     // shared memory carve-up (byte offsets from the 128-aligned base)
     uint32_t off_a, off_b, off_img, off_raw, off_wc, off_imax;
-    uint32_t b_buf_bytes;          // one im2col buffer: G + 1 planes
+    uint32_t b_buf_bytes;          // one im2col buffer: the images of one tile + 1 spare plane + 32 rows
     uint32_t raw_buf_bytes;        // T * 128 * 16
     size_t n_groups;
+    uint32_t n_wg;                 // consumer warpgroups (3 when the im2col buffers of three fit in shared memory, else 2)
 };
 
 __device__ __forceinline__ uint32_t pack_relu_u16(int hi, int lo) {
@@ -99,7 +101,7 @@ __device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, u
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[4 * q]), "=r"(r[4 * q + 1]), "=r"(r[4 * q + 2]), "=r"(r[4 * q + 3])
                              : "r"(tm + 64 * y + 16 * q));
         } else {
-            tmem_ld_x16(tm + y * 16, r);
+            tmem_ld_x16(tm + ((y >> 2) & 1) * 64 + (y & 3) * 16, r);   // piece y / 4 lives in buffer (y / 4) & 1
         }
     };
     auto wait_row = [&](uint32_t (&r)[16]) { if (!kFromSmem) tmem_ld_wait_x16(r); };
@@ -108,8 +110,11 @@ __device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, u
     int c3e[4];
     uint32_t PE[6][3], PO[6][3];   // kConv3Packed: pooled rows as uint16 pairs
     uint32_t cur[16], nxt[16];
+    // Accumulator pieces: conv1 rows 4k .. 4k+3 of a tile are piece k (64 columns), pieces alternate between the warpgroup's two
+    // TMEM buffers.  Buffer b is filled twice per tile (pieces b and b + 2): its barrier phases are 2 t and 2 t + 1 for tile t, so
+    // the wait parity of piece k is (k >> 1) whatever the tile -- compile-time constants in this unrolled code.
     if (!kFromSmem) {
-        mbar_wait_a(bar_full0, parity, err, 11);
+        mbar_wait_a(bar_full0, 0, err, 11);
         tc_fence_after();
     }
     load_row(0, cur);
@@ -117,8 +122,8 @@ __device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, u
 #pragma unroll
     for (int y = 0; y < 14; y++) {
         if (y + 1 < 14) {
-            if (y + 1 == 7 && !kFromSmem) {
-                mbar_wait_a(bar_full1, parity, err, 12);
+            if (((y + 1) & 3) == 0 && !kFromSmem) {   // first row of the next piece
+                mbar_wait_a((((y + 1) >> 2) & 1) ? bar_full1 : bar_full0, ((y + 1) >> 3) & 1, err, 12);
                 tc_fence_after();
             }
             load_row(y + 1, nxt);   // prefetch the next conv1 row while this one is processed
@@ -216,9 +221,9 @@ __device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, u
         }
         if (y + 1 < 14) {
             wait_row(nxt);
-            if (!kFromSmem && (y + 1 == 6 || y + 1 == 13)) {   // the last row of an accumulator half is in registers: the half may be overwritten
+            if (!kFromSmem && ((((y + 1) & 3) == 3) || y + 1 == 13)) {   // the last row of a piece is in registers: its buffer may be overwritten
                 tc_fence_before();
-                mbar_arrive_a(y + 1 == 6 ? bar_free0 : bar_free1);
+                mbar_arrive_a((((y + 1) >> 2) & 1) ? bar_free1 : bar_free0);
             }
 #pragma unroll
             for (int x = 0; x < 16; x++) cur[x] = nxt[x];
@@ -227,31 +232,31 @@ __device__ __forceinline__ void cnn_tile_tail(uint32_t tm, uint32_t bar_full0, u
 }
 
 template <bool kConv3Packed>
-__global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __grid_constant__ CnnTcParams P) {
+__global__ void __launch_bounds__(kCnnTcMaxThreads, 1) k_cnn_frontend16_tc(const __grid_constant__ CnnTcParams P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[2][2], bar_free[2][2];   // [warpgroup][accumulator half]
-    __shared__ __align__(8) uint64_t bar_group[2];                     // [warpgroup]: a group's per-image maxima are published
+    __shared__ __align__(8) uint64_t bar_full[kMaxCnnWG][2], bar_free[kMaxCnnWG][2];   // [warpgroup][accumulator buffer]
+    __shared__ __align__(8) uint64_t bar_group[kMaxCnnWG];                              // [warpgroup]: a group's per-image maxima are published
     __shared__ uint32_t tmem_base_s;
     const uint32_t t = threadIdx.x, lane = t & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, t >> 5, 0);
     uint8_t *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    const uint32_t C = P.C, G = P.G, T = P.T;
+    const uint32_t C = P.C, G = P.G, T = P.T, n_wg = P.n_wg, n_thr = blockDim.x;
 
     // ---- one-time setup: barriers, TMEM, the A operand (w1 per tile phase), per-channel tail weights
     if (t == 0) {
 #pragma unroll
-        for (int g = 0; g < 2; g++)
+        for (int g = 0; g < (int)kMaxCnnWG; g++) {
 #pragma unroll
             for (int h = 0; h < 2; h++) { mbar_init(&bar_full[g][h], 1); mbar_init(&bar_free[g][h], 128); }
-        mbar_init(&bar_group[0], 128);
-        mbar_init(&bar_group[1], 128);
+            mbar_init(&bar_group[g], 128);
+        }
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc<512>(&tmem_base_s);
+    if (warp == n_wg * 4) tmem_alloc<512>(&tmem_base_s);
     {
         uint4 *a4 = reinterpret_cast<uint4 *>(base + P.off_a);
         const uint32_t total = T * P.n_chunks_max * 128;   // 16-byte rows
-        for (uint32_t i = t; i < total; i += kCnnTcThreads) {
+        for (uint32_t i = t; i < total; i += n_thr) {
             const uint32_t phase = i / (P.n_chunks_max * 128), rem = i % (P.n_chunks_max * 128), chunk = rem >> 7, r = rem & 127;
             const uint32_t item = phase * 128 + r, il = item / C, ch = item % C, i0 = (phase * 128) / C;
             uint32_t q[4] = {0, 0, 0, 0};
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
             a4[i] = make_uint4(q[0], q[1], q[2], q[3]);   // [phase][chunk][row][16 B]
         }
         int *wc = reinterpret_cast<int *>(base + P.off_wc);
-        for (uint32_t ch = t; ch < C; ch += kCnnTcThreads) {
+        for (uint32_t ch = t; ch < C; ch += n_thr) {
             const int8_t *b = P.w2 + ch * 9, *c = P.w3 + ch * 9;
             auto pair = [](int8_t lo, int8_t hi) { return (int)((uint32_t)(uint8_t)lo | ((uint32_t)(uint8_t)hi << 8)); };
             int *o = wc + ch * 16;
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
             }
         }
         int *imax = reinterpret_cast<int *>(base + P.off_imax);
-        for (uint32_t i = t; i < 2 * 3 * 8; i += kCnnTcThreads) imax[i] = 0;
+        for (uint32_t i = t; i < kMaxCnnWG * 3 * 8; i += n_thr) imax[i] = 0;
     }
     fence_proxy_async_smem();   // the tensor core (async proxy) reads A
     tc_fence_before();
@@ -289,41 +294,47 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp >= 8) {
-        // ======================= producer pair of warpgroup g: warps 8 + g (also the MMA issuer) and 10 + g =======================
-        // Four helper warps, one per SM sub-partition, so that every sub-partition carries the same load (two consumer warps + half
-        // a producer): the consumers of a warpgroup advance in lockstep through the accumulator barriers, and a sub-partition that
-        // also hosted a whole producer used to set the pace for all four.  The two warps of a pair split a group's im2col tasks
-        // and meet at a 64-thread named barrier (id 1 + g).
-        const uint32_t g = (warp - 8) & 1, helper = (warp - 8) >> 1, lane64 = lane + 32 * helper;
+    if (warp >= n_wg * 4) {
+        // ======================= producer + MMA issuer of warpgroup g (one warp) =======================
+        const uint32_t g = warp - n_wg * 4;
         const bool leader = elect_one();
         uint32_t *s_img = reinterpret_cast<uint32_t *>(base + P.off_img + g * (8 * 256 + 64));
-        const uint32_t n_ld = (G * 16 + 63) / 64;   // 16-byte loads per lane and group (<= 2)
-        const uint32_t idesc = make_idesc_i8(128, kHalfCols);
+        const uint32_t n_ld = (G * 16 + 31) / 32;   // 16-byte loads per lane and group (<= 4)
+        const uint32_t idesc = make_idesc_i8(128, kPieceCols);
         const uint32_t a_base = smem_u32(base + P.off_a);
-        uint32_t free_phase = 0;   // one bit per half; a fresh barrier passes a wait on parity 1
-        uint4 img_regs[2];
-        auto load_group = [&](size_t grp) {   // global -> registers (latency hidden behind the previous group's work)
+        // The im2col operand is built per TILE: the images a tile touches (up to 128 / C + 1 of them; tiles of one group overlap in
+        // at most one image, which is then built twice), double-buffered, so that the buffers of three warpgroups fit in shared
+        // memory for every channel count.
+        uint4 img_regs[4];
+        auto unit_images = [&](size_t grp, uint32_t tau, size_t &first, uint32_t &count) {
+            const uint32_t i0 = (tau * 128) / C, i1 = (tau * 128 + 127) / C;
+            first = grp * G + i0;
+            count = i1 - i0 + 1;
+        };
+        auto load_unit = [&](size_t grp, uint32_t tau) {   // global -> registers (latency hidden behind the previous tile's work)
+            size_t first; uint32_t count;
+            unit_images(grp, tau, first, count);
 #pragma unroll
-            for (uint32_t k = 0; k < 2; k++) {
+            for (uint32_t k = 0; k < 4; k++) {
                 img_regs[k] = make_uint4(0, 0, 0, 0);
-                const uint32_t idx = k * 64 + lane64;   // uint4 index inside the group: image = idx / 16
-                if (k < n_ld && idx < G * 16 && grp * G + idx / 16 < P.n)
-                    img_regs[k] = reinterpret_cast<const uint4 *>(P.images)[grp * G * 16 + idx];
+                const uint32_t idx = k * 32 + lane;   // uint4 index inside the unit: image = idx / 16
+                if (idx < count * 16 && first + idx / 16 < P.n)
+                    img_regs[k] = reinterpret_cast<const uint4 *>(P.images)[first * 16 + idx];
             }
         };
-        auto build_group = [&](uint32_t buf) {   // registers -> s_img -> im2col planes of buffer buf, both warps of the pair
+        auto build_unit = [&](uint32_t buf, uint32_t count) {   // registers -> s_img -> im2col planes of buffer buf
+            __syncwarp();
 #pragma unroll
-            for (uint32_t k = 0; k < 2; k++) {
-                const uint32_t idx = k * 64 + lane64;
-                if (k < n_ld && idx < G * 16) reinterpret_cast<uint4 *>(s_img)[idx] = img_regs[k];
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t idx = k * 32 + lane;
+                if (idx < count * 16) reinterpret_cast<uint4 *>(s_img)[idx] = img_regs[k];
             }
-            named_bar_sync(1 + g, 64);   // the group's images are staged
+            __syncwarp();
             uint8_t *bbuf = base + P.off_b + (g * 2 + buf) * P.b_buf_bytes;
             // one task = four consecutive positions (y, 4 xg .. 4 xg + 3) of one image: six shared-memory words (two per image row)
             // feed four 16-byte im2col rows; 56 tasks per image (14 rows x 4 column groups, the last group holds x = 12, 13 only)
 #pragma unroll 1
-            for (uint32_t task = lane64; task < G * 56; task += 64) {
+            for (uint32_t task = lane; task < count * 56; task += 32) {
                 const uint32_t im = task / 56, rem = task - im * 56, y = rem >> 2, xg = rem & 3;
                 const uint32_t *row = s_img + im * 64 + y * 4 + xg;
                 const uint32_t a0 = row[0], a1 = row[1], b0 = row[4], b1 = row[5], c0 = row[8], c1 = row[9];
@@ -344,57 +355,73 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
                 }
             }
             fence_proxy_async_smem();   // the MMAs (async proxy) read what these generic-proxy stores wrote
-            named_bar_sync(1 + g, 64);   // both halves of the build are done (and s_img may be overwritten)
+            __syncwarp();
         };
-        auto issue_tile = [&](uint32_t buf, uint32_t tau) {   // issuer warp only
-            const uint32_t i0 = (tau * 128) / C, i1 = (tau * 128 + 127) / C;
-            const uint32_t n_k = (i1 - i0 + 2) / 2;   // K-steps of 32 bytes = two image slots
-            const uint32_t b_base = smem_u32(base + P.off_b + (g * 2 + buf) * P.b_buf_bytes) + i0 * kPlaneBytes;
-            for (uint32_t h = 0; h < 2; h++) {
-                mbar_wait_relaxed(&bar_free[g][h], ((free_phase >> h) & 1) ^ 1, P.err, 13);
-                free_phase ^= 1u << h;
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + g * 224 + h * kHalfCols;
-                for (uint32_t s = 0; s < n_k; s++) {
-                    const uint64_t ad = make_smem_desc(a_base + tau * P.a_phase_bytes + s * 2 * P.a_plane_bytes, P.a_plane_bytes, 128, UMMA_LAYOUT_NONE);
-                    const uint64_t bd = make_smem_desc(b_base + s * 2 * kPlaneBytes + h * kHalfCols * 16, kPlaneBytes, 128, UMMA_LAYOUT_NONE);
-                    if (leader) umma_i8_ss(d_tmem, ad, bd, idesc, s != 0);
-                }
-                if (leader) umma_commit(&bar_full[g][h]);
-                __syncwarp();
+        // piece k of a tile (conv1 rows 4k .. 4k+3 = im2col rows 64k .. 64k+63; the last piece runs 32 rows past the plane into
+        // whatever follows -- rows nobody reads) goes to accumulator buffer k & 1 once its previous occupant (piece k - 2 of this
+        // tile, or piece k + 2 of the tile before) has been drained: the (2 t + (k >> 1))-th fill waits for drain number one less,
+        // i.e. parity (k >> 1) ^ 1 -- a fresh barrier passes a wait on parity 1
+        auto issue_piece = [&](uint32_t buf, uint32_t tau, uint32_t count, uint32_t k) {
+            const uint32_t n_k = (count + 1) / 2;   // K-steps of 32 bytes = two image slots
+            const uint32_t b_base = smem_u32(base + P.off_b + (g * 2 + buf) * P.b_buf_bytes);
+            const uint32_t h = k & 1;
+            mbar_wait_relaxed(&bar_free[g][h], (k >> 1) ^ 1, P.err, 13);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + g * 2 * kPieceCols + h * kPieceCols;
+            for (uint32_t s = 0; s < n_k; s++) {
+                const uint64_t ad = make_smem_desc(a_base + tau * P.a_phase_bytes + s * 2 * P.a_plane_bytes, P.a_plane_bytes, 128, UMMA_LAYOUT_NONE);
+                const uint64_t bd = make_smem_desc(b_base + s * 2 * kPlaneBytes + k * kPieceCols * 16, kPlaneBytes, 128, UMMA_LAYOUT_NONE);
+                if (leader) umma_i8_ss(d_tmem, ad, bd, idesc, s != 0);
             }
+            if (leader) umma_commit(&bar_full[g][h]);
+            __syncwarp();
         };
-        // groups of this warpgroup: j = (k * gridDim + blockIdx) * 2 + g
-        const size_t stride = (size_t)gridDim.x * 2;
-        size_t j = (size_t)blockIdx.x * 2 + g;
-        uint32_t buf = 0;
+        // tiles of this warpgroup, in order: groups j = (k * gridDim + blockIdx) * n_wg + g, tiles tau = 0 .. T-1 of each
+        const size_t stride = (size_t)gridDim.x * n_wg;
+        size_t j = (size_t)blockIdx.x * n_wg + g;
+        uint32_t tau = 0, buf = 0;
+        auto advance = [&](size_t &jj, uint32_t &tt) { if (++tt == T) { tt = 0; jj += stride; } };
         if (j < P.n_groups) {
-            load_group(j);
-            build_group(0);
-            if (j + stride < P.n_groups) load_group(j + stride);
+            size_t first; uint32_t count;
+            unit_images(j, 0, first, count);
+            load_unit(j, 0);
+            build_unit(0, count);
+            size_t jn = j; uint32_t tn = 0;
+            advance(jn, tn);
+            if (jn < P.n_groups) load_unit(jn, tn);
         }
-        for (; j < P.n_groups; j += stride, buf ^= 1) {
-            if (!helper) issue_tile(buf, 0);
-            // Every MMA of the group before this one has completed (its last accumulator halves were drained before the waits
-            // above passed): the other im2col buffer is free for the next group.  The helper learns it at this barrier.
-            named_bar_sync(1 + g, 64);
-            if (j + stride < P.n_groups) {
-                build_group(buf ^ 1);
-                if (j + 2 * stride < P.n_groups) load_group(j + 2 * stride);
+        while (j < P.n_groups) {
+            size_t first; uint32_t count;
+            unit_images(j, tau, first, count);
+            issue_piece(buf, tau, count, 0);
+            issue_piece(buf, tau, count, 1);
+            // Every MMA of the tile before this one has completed (its pieces 2 and 3 were drained before the two waits above
+            // passed): the other im2col buffer is free for the next tile.
+            size_t jn = j; uint32_t tn = tau;
+            advance(jn, tn);
+            if (jn < P.n_groups) {
+                size_t nfirst; uint32_t ncount;
+                unit_images(jn, tn, nfirst, ncount);
+                build_unit(buf ^ 1, ncount);
+                size_t j2 = jn; uint32_t t2 = tn;
+                advance(j2, t2);
+                if (j2 < P.n_groups) load_unit(j2, t2);
             }
-            if (!helper) for (uint32_t tau = 1; tau < T; tau++) issue_tile(buf, tau);
+            issue_piece(buf, tau, count, 2);
+            issue_piece(buf, tau, count, 3);
+            j = jn; tau = tn; buf ^= 1;
         }
     } else {
         // ======================= consumer warpgroup g: thread r = TMEM lane r =======================
         const uint32_t g = warp >> 2, r = t & 127;
-        const uint32_t tm = tmem_base + (((warp & 3) * 32) << 16) + g * 224;
+        const uint32_t tm = tmem_base + (((warp & 3) * 32) << 16) + g * 2 * kPieceCols;
         const uint32_t bf0 = smem_u32(&bar_full[g][0]), bf1 = smem_u32(&bar_full[g][1]);
         const uint32_t be0 = smem_u32(&bar_free[g][0]), be1 = smem_u32(&bar_free[g][1]);
         const uint32_t bgrp = smem_u32(&bar_group[g]);
         const int *wc = reinterpret_cast<const int *>(base + P.off_wc);
         int *imax = reinterpret_cast<int *>(base + P.off_imax) + g * 24;   // [3][8]
         uint32_t parity = 0, gcount = 0;
-        const size_t stride = (size_t)gridDim.x * 2;
+        const size_t stride = (size_t)gridDim.x * n_wg;
         // ReLUNorm over the C*4 features of each image (dll.c:80) needs the maximum over ALL channels of the image, i.e. over other
         // threads' results.  It runs one group late: a group's threads publish their maxima (shared-memory atomicMax) and ARRIVE on
         // the warpgroup's mbarrier without waiting; the wait comes a whole group of work later, when the phase has long completed,
@@ -427,7 +454,7 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
         };
         load_weights(ch_one);
         size_t j_prev = 0;
-        for (size_t j = (size_t)blockIdx.x * 2 + g; j < P.n_groups; j_prev = j, j += stride, gcount++) {
+        for (size_t j = (size_t)blockIdx.x * n_wg + g; j < P.n_groups; j_prev = j, j += stride, gcount++) {
             int4 *raw = reinterpret_cast<int4 *>(base + P.off_raw + (g * 2 + (gcount & 1)) * P.raw_buf_bytes);
             for (uint32_t tau = 0; tau < T; tau++, parity ^= 1) {
                 const uint32_t item = tau * 128 + r;
@@ -459,7 +486,7 @@ __global__ void __launch_bounds__(kCnnTcThreads, 1) k_cnn_frontend16_tc(const __
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem_base);
+    if (warp == n_wg * 4) tmem_dealloc<512>(tmem_base);
 }
 
 static uint32_t gcd_u32(uint32_t a, uint32_t b) { return b ? gcd_u32(b, a % b) : a; }
@@ -475,18 +502,23 @@ static size_t cnn_tc_plan(uint32_t channels, uint32_t xy, CnnTcParams &p) {
     p.n_chunks_max = (max_imgs + 1) / 2 * 2;
     p.a_plane_bytes = 128 * 16;
     p.a_phase_bytes = p.n_chunks_max * p.a_plane_bytes;
-    p.b_buf_bytes = (p.G + 1) * kPlaneBytes;   // + one spare plane: an odd image count reads one zero-weighted chunk past the last image
+    // one tile's images + one spare plane (an odd image count reads one zero-weighted chunk past the last image) + 32 rows (the
+    // last accumulator piece of a tile covers im2col rows 192..255 of a 224-row plane)
+    p.b_buf_bytes = (max_imgs + 1) * kPlaneBytes + 32 * 16;
     p.raw_buf_bytes = p.T * 128 * 16;
-    uint32_t off = 0;
-    auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 127) / 128 * 128; return o; };
-    p.off_a = take(p.T * p.a_phase_bytes);
-    p.off_b = take(4 * p.b_buf_bytes);
-    p.off_img = take(2 * (8 * 256 + 64));
-    p.off_raw = take(4 * p.raw_buf_bytes);
-    p.off_wc = take(channels * 64);
-    p.off_imax = take(2 * 3 * 8 * 4);
-    const size_t smem = (size_t)off + 128;
-    return smem <= 226 * 1024 ? smem : 0;
+    for (p.n_wg = kMaxCnnWG; p.n_wg >= 2; p.n_wg--) {   // three consumer warpgroups when their im2col buffers fit, else two
+        uint32_t off = 0;
+        auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 127) / 128 * 128; return o; };
+        p.off_a = take(p.T * p.a_phase_bytes);
+        p.off_b = take(p.n_wg * 2 * p.b_buf_bytes);
+        p.off_img = take(p.n_wg * (8 * 256 + 64));
+        p.off_raw = take(p.n_wg * 2 * p.raw_buf_bytes);
+        p.off_wc = take(channels * 64);
+        p.off_imax = take(kMaxCnnWG * 3 * 8 * 4);
+        const size_t smem = (size_t)off + 128;
+        if (smem <= 226 * 1024) return smem;
+    }
+    return 0;
 }
 
 bool cnn_frontend_tc_supported(uint32_t channels, uint32_t xy) {
@@ -513,10 +545,11 @@ bool launch_cnn_frontend_tc(const int8_t *images, const int8_t *w1, const int8_t
         }
         granted = smem;
     }
-    const size_t want = (p.n_groups + 1) / 2;
+    const size_t want = (p.n_groups + p.n_wg - 1) / p.n_wg;
     const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)sm_count);
-    if (conv3_fits_u16) k_cnn_frontend16_tc<true><<<grid, kCnnTcThreads, smem, st>>>(p);
-    else k_cnn_frontend16_tc<false><<<grid, kCnnTcThreads, smem, st>>>(p);
+    const unsigned threads = p.n_wg * 160;   // 4 consumer warps + 1 producer warp per warpgroup
+    if (conv3_fits_u16) k_cnn_frontend16_tc<true><<<grid, threads, smem, st>>>(p);
+    else k_cnn_frontend16_tc<false><<<grid, threads, smem, st>>>(p);
     return true;
 }
 
