@@ -39,7 +39,7 @@ MAX_GATHER_DST = 8
 class BnmGather(C.Structure):
     """bnm_gather (include/bitnetmcu_b200.h): destinations of the fused result exchange."""
     _fields_ = [("n_labels_dst", C.c_uint32), ("n_logits_dst", C.c_uint32), ("labels_dst", C.c_void_p * MAX_GATHER_DST),
-                ("logits_dst", C.c_void_p * MAX_GATHER_DST), ("row_offset", C.c_size_t)]
+                ("logits_dst", C.c_void_p * MAX_GATHER_DST), ("row_offset", C.c_size_t), ("labels_u8", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 _lib = None

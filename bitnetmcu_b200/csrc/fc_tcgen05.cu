@@ -60,6 +60,7 @@ struct ChainParams {
     uint32_t *lab_dst[kMaxGatherDst];
     int32_t *log_dst[kMaxGatherDst];
     size_t row0;
+    uint32_t lab_u8;                  // gather launches: lab_dst are uint8 buffers (one byte per label)
     uint32_t off_gstage;              // gather launches: smem offset of the per-warp staging rows for the bulk peer stores (0: none)
 };
 
@@ -507,7 +508,10 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                         }
                         if (full_tile || img < P.n) {
                             if (P.labels) P.labels[img] = pos;
-                            for (uint32_t d = 0; kGather && d < P.n_lab_dst; d++) P.lab_dst[d][P.row0 + img] = pos;
+                            for (uint32_t d = 0; kGather && d < P.n_lab_dst; d++) {
+                                if (P.lab_u8) reinterpret_cast<uint8_t *>(P.lab_dst[d])[P.row0 + img] = (uint8_t)pos;
+                                else P.lab_dst[d][P.row0 + img] = pos;
+                            }
                         }
                     }
                     BNM_TRACE_POINT();   // step end
@@ -690,11 +694,14 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     p.n = n;
     p.n_lab_dst = p.n_log_dst = 0;
     p.row0 = 0;
+    p.lab_u8 = 0;
     if (gather) {
         if (gather->n_labels_dst > (uint32_t)kMaxGatherDst || gather->n_logits_dst > (uint32_t)kMaxGatherDst) return -5;
         p.n_lab_dst = gather->n_labels_dst;
         p.n_log_dst = gather->n_logits_dst;
         p.row0 = gather->row_offset;
+        p.lab_u8 = gather->labels_u8 && p.n_classes <= 255;
+        if (gather->labels_u8 && !p.lab_u8) return -5;
         for (uint32_t d = 0; d < p.n_lab_dst; d++) p.lab_dst[d] = gather->labels_dst[d];
         for (uint32_t d = 0; d < p.n_log_dst; d++) p.log_dst[d] = gather->logits_dst[d];
     }

@@ -16,6 +16,7 @@ struct GatherDst {
     uint32_t *labels_dst[kMaxGatherDst];
     int32_t *logits_dst[kMaxGatherDst];
     size_t row_offset;
+    uint32_t labels_u8, reserved;
 };
 
 // One fully connected layer, decoded once at model build into dense int8 planes (K3 "weight pre-decode").

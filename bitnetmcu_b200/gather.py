@@ -51,27 +51,34 @@ class PeerGatherBuffers:
             self._local_ptrs.append(p.value)
             return p.value
         self.lab_ptr = alloc(rows * 4)
+        self.lab8_ptr = alloc(rows)                  # one byte per label (n_classes <= 255): a quarter of the NVLink traffic
         self.log_ptr = alloc(rows * n_classes * 4) if with_logits else None
 
         def export(ptr):
             h = (C.c_ubyte * 64)()
             _lib.check(self.lib.bnm_ipc_export(C.c_void_p(ptr), h), "bnm_ipc_export")
             return bytes(h)
-        mine = {"lab": export(self.lab_ptr), "log": export(self.log_ptr) if with_logits else None}
+        mine = {"lab": export(self.lab_ptr), "lab8": export(self.lab8_ptr), "log": export(self.log_ptr) if with_logits else None}
         allh: List[Optional[dict]] = [None] * self.world
         dist.all_gather_object(allh, mine, group=group)
         self._opened = []
         self.lab_dst: List[int] = []
+        self.lab8_dst: List[int] = []
         self.log_dst: List[int] = []
         for r, h in enumerate(allh):
             if r == self.rank:
                 self.lab_dst.append(self.lab_ptr)
+                self.lab8_dst.append(self.lab8_ptr)
                 self.log_dst.append(self.log_ptr or 0)
                 continue
             p = C.c_void_p()
             _lib.check(self.lib.bnm_ipc_open(device, (C.c_ubyte * 64).from_buffer_copy(h["lab"]), C.byref(p)), "bnm_ipc_open")
             self._opened.append(p.value)
             self.lab_dst.append(p.value)
+            p8 = C.c_void_p()
+            _lib.check(self.lib.bnm_ipc_open(device, (C.c_ubyte * 64).from_buffer_copy(h["lab8"]), C.byref(p8)), "bnm_ipc_open")
+            self._opened.append(p8.value)
+            self.lab8_dst.append(p8.value)
             if with_logits:
                 q = C.c_void_p()
                 _lib.check(self.lib.bnm_ipc_open(device, (C.c_ubyte * 64).from_buffer_copy(h["log"]), C.byref(q)), "bnm_ipc_open")
@@ -81,14 +88,16 @@ class PeerGatherBuffers:
                 self.log_dst.append(0)
         dev = torch.device("cuda", device)
         self.labels = torch.as_tensor(_DevArray(self.lab_ptr, (rows,), "<i4", self), device=dev)
+        self.labels_u8 = torch.as_tensor(_DevArray(self.lab8_ptr, (rows,), "|u1", self), device=dev)
         self.logits = torch.as_tensor(_DevArray(self.log_ptr, (rows, n_classes), "<i4", self), device=dev) if with_logits else None
 
-    def spec(self, labels_to: Optional[List[int]], logits_to: Optional[List[int]]):
-        """bnm_gather for this rank: destination ranks of the labels / logits (None = nobody)."""
+    def spec(self, labels_to: Optional[List[int]], logits_to: Optional[List[int]], labels_u8: bool = False):
+        """bnm_gather for this rank: destination ranks of the labels / logits (None = nobody); labels_u8: one byte per label."""
         g = _lib.BnmGather()
         g.row_offset = self.rank * self.n
+        g.labels_u8 = 1 if labels_u8 else 0
         for k, r in enumerate(labels_to or []):
-            g.labels_dst[k] = self.lab_dst[r]
+            g.labels_dst[k] = (self.lab8_dst if labels_u8 else self.lab_dst)[r]
         g.n_labels_dst = len(labels_to or [])
         for k, r in enumerate(logits_to or []):
             g.logits_dst[k] = self.log_dst[r]
@@ -104,10 +113,10 @@ class PeerGatherBuffers:
         self._local_ptrs = []
 
 
-def infer_gather(eng, images, logits, labels, buffers: PeerGatherBuffers, labels_to, logits_to, stream: int) -> None:
+def infer_gather(eng, images, logits, labels, buffers: PeerGatherBuffers, labels_to, logits_to, stream: int, labels_u8: bool = False) -> None:
     """``Engine.infer_device`` whose epilogue also stores this rank's rows into the gather buffers of the ranks listed in
     ``labels_to`` / ``logits_to`` (pass this rank's own slice of its buffer as ``logits`` / ``labels`` and leave it out of the lists)."""
-    g = buffers.spec(labels_to, logits_to)
+    g = buffers.spec(labels_to, logits_to, labels_u8)
     lab_ptr = C.c_void_p(labels.data_ptr()) if labels is not None else None
     _lib.check(eng.lib.bnm_infer_batch_device_gather(eng.handle, C.c_void_p(images.data_ptr()), images.shape[0], C.c_void_p(logits.data_ptr()),
                                                      lab_ptr, C.byref(g), C.c_void_p(stream)), "bnm_infer_batch_device_gather")
@@ -152,8 +161,8 @@ def bench_gathers(ctx, eng, db, ms_compute: float) -> dict:
         my_log = bufs.logits[rank * n:(rank + 1) * n]
         my_lab = bufs.labels[rank * n:(rank + 1) * n]
 
-        def run(labels_to, logits_to):
-            return timed(lambda i: infer_gather(eng, db.d_in[i & 1], my_log, my_lab, bufs, labels_to, logits_to, st))
+        def run(labels_to, logits_to, u8=False):
+            return timed(lambda i: infer_gather(eng, db.d_in[i & 1], my_log, my_lab, bufs, labels_to, logits_to, st, labels_u8=u8))
 
         def check(t_all, mine):   # after the barrier inside timed(): every rank's slice of MY buffer equals that rank's own slice
             theirs = [torch.empty_like(mine) for _ in range(world)]
@@ -163,6 +172,10 @@ def bench_gathers(ctx, eng, db, ms_compute: float) -> dict:
         out["value_with_label_gather"] = world * n / (ms_lab * 1e-3)
         out["label_gather_ms_per_step"] = ms_lab
         out["label_gather_complete_and_correct"] = check(bufs.labels, my_lab)
+        ms_lab8 = run(list(range(world)), None, u8=True)   # one byte per label, every rank incl. this one (its own uint32 labels stay local)
+        out["value_with_label_gather_u8"] = world * n / (ms_lab8 * 1e-3)
+        out["label_gather_u8_ms_per_step"] = ms_lab8
+        out["label_gather_u8_complete_and_correct"] = check(bufs.labels_u8, my_lab.to(torch.uint8))
         ms_log_all = run(peers, peers)
         out["value_with_logits_gather"] = world * n / (ms_log_all * 1e-3)
         out["logits_gather_ms_per_step"] = ms_log_all

@@ -154,6 +154,8 @@ typedef struct bnm_gather {
     uint32_t *labels_dst[BNM_MAX_GATHER_DST];
     int32_t *logits_dst[BNM_MAX_GATHER_DST];   /* 8-byte aligned */
     size_t row_offset;
+    uint32_t labels_u8;   /* non-zero: labels_dst are uint8 [rows] buffers (one byte per label, n_classes <= 255): a quarter of the NVLink traffic */
+    uint32_t reserved;
 } bnm_gather;
 BNM_API int bnm_infer_batch_device_gather(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels,
                                           const bnm_gather *gather, void *stream);

@@ -601,6 +601,17 @@ def _gather_case(lib, oracle, name, n, dst_device):
                                                      Ct.c_void_p(d_lab.data_ptr()), Ct.byref(g), Ct.c_void_p(s.cuda_stream)), "gather")
         s.synchronize()
     assert np.array_equal(d_log.cpu().numpy(), want) and np.array_equal(d_lab.cpu().numpy().astype(np.uint32), want_lab)
+    # one byte per label (bnm_gather.labels_u8)
+    dst8 = torch.full((rows,), 201, dtype=torch.uint8, device=f"cuda:{dst_device}")
+    g8 = _lib.BnmGather()
+    g8.n_labels_dst, g8.n_logits_dst, g8.row_offset, g8.labels_u8 = 1, 0, off, 1
+    g8.labels_dst[0] = dst8.data_ptr()
+    with torch.cuda.device(0):
+        _lib.check(lib.bnm_infer_batch_device_gather(e.handle, Ct.c_void_p(d_img.data_ptr()), n, Ct.c_void_p(d_log.data_ptr()),
+                                                     Ct.c_void_p(d_lab.data_ptr()), Ct.byref(g8), Ct.c_void_p(s.cuda_stream)), "gather u8")
+        s.synchronize()
+    g8h = dst8.cpu().numpy()
+    assert np.array_equal(g8h[off:off + n], want_lab.astype(np.uint8)) and (g8h[:off] == 201).all() and (g8h[off + n:] == 201).all()
     for k in range(2):
         gl, gb = dst_log[k].cpu().numpy(), dst_lab[k].cpu().numpy()
         assert np.array_equal(gl[off:off + n], want), (name, n, dst_device, k)
