@@ -10,6 +10,7 @@ rank with no data-path collective (weak scaling: 1M images per GPU).  Prints ONE
 
 value        : whole-job images/s, device-timed (CUDA events), max over ranks, inputs resident in HBM, PLAIN launches
                (ordinary stream semantics: what a drop-in caller gets by default)
+value_two_streams : same steps, plain launches alternating between two streams (ordinary CUDA semantics for independent batches)
 value_overlapped_launches : same steps with BNM_OPT_LAUNCH_OVERLAP = 2 (consecutive launches declared independent; the
                bench double-buffers inputs and outputs, which is what that mode asks for)
 value_sustained: >= 1 s of back-to-back plain launches, with the nvidia-smi clock sampler covering THAT region
@@ -560,6 +561,27 @@ def main():
     snap_plain = db.snapshot()
     launches = args.steps * eng.launch_count(n)
 
+    # ---- the same steps, still plain launches, alternating between TWO streams: the ordinary CUDA way for a caller to say that
+    # consecutive (double-buffered) batches are independent -- the tail of one launch then overlaps the head of the next
+    ms_two = None
+    try:
+        two = [torch.cuda.Stream(device=ctx.dev), torch.cuda.Stream(device=ctx.dev)]
+
+        def step2(i):
+            eng.infer_device(db.d_in[i & 1], db.d_logits[i & 1], db.d_labels[i & 1], two[i & 1].cuda_stream)
+        for i in range(4):
+            step2(i)
+        ctx.barrier()
+        t0e, e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record(two[0]); two[1].wait_event(t0e)
+        for i in range(args.steps):
+            step2(i)
+        e0.record(two[0]); e1.record(two[1])
+        ctx.barrier()
+        ms_two = ctx.max_over_ranks(max(t0e.elapsed_time(e0), t0e.elapsed_time(e1)) / args.steps)
+    except Exception as ex:
+        log("two-stream measurement failed:", ex)
+
     # ---- the same steps with consecutive launches declared independent (BNM_OPT_LAUNCH_OVERLAP = 2)
     eng.set_option(_lib.OPT_LAUNCH_OVERLAP, 2)
     ms_overlap, _ = ctx.timed_steps(db.step, args.steps, 3)
@@ -610,6 +632,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": gbs(kernel_ms), "peak": peak, "unit": "GB/s", "frac": gbs(kernel_ms) / peak,
                 "traffic": traffic_for(args.model, n), "kernel": "fc_chain_kernel" if eng.active_path == _lib.PATH_TCGEN05 else "layer kernels",
                 "kernel_ms": kernel_ms, "kernel_ms_isolated_launch": kernel_ms_isolated,
+                "frac_two_streams": (gbs(ms_two) / peak) if (ms_two and single_kernel_step) else None,
                 "frac_overlapped_launches": gbs(ms_overlap) / peak if single_kernel_step else None,
                 "frac_sustained": gbs(sus_ms / n_sus) / peak if single_kernel_step else None,
                 "algorithmic_bytes_per_image": bytes_per_image, "peak_source": peak_src,
@@ -685,6 +708,7 @@ def main():
                        "path": "tcgen05" if eng.active_path == _lib.PATH_TCGEN05 else "layers",
                        "launch_semantics": "plain launches (BNM_OPT_LAUNCH_OVERLAP = 0): ordinary stream semantics",
                        "host_numa": ctx.numa},
+            "value_two_streams": (world * n / (ms_two * 1e-3)) if ms_two else None,
             "value_overlapped_launches": world * n / (ms_overlap * 1e-3),
             "value_sustained": sustained,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,

@@ -112,3 +112,17 @@ def test_parser_on_every_shipped_reference_header():
         assert m.fc_layers and m.macs_per_image > 0
     imgs, labels = M.parse_test_data_header(os.path.join(REF, "BitNetMCU_MNIST_test_data.h"))
     assert imgs.shape == (10, 256) and labels.tolist() == [3, 2, 0, 9, 0, 6, 9, 2, 7, 7] and imgs[0, 0] == -20   # 0xEC narrowed to int8
+
+
+def test_blob_roundtrip_names_layers_like_the_reference_harness():
+    """the BNM1 blob stores no layer names; Model.load assigns the names the reference's dll.c compiles against
+    (FC: L1.., CNN: L2, L4, L6, L7, L9, L11, L13, L15 -- BitNetMCU_MNIST_dll.c:48-121), so write_header output links unchanged."""
+    from bitnetmcu_b200.model import Model
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fc = Model.load(os.path.join(root, "tests", "golden", "models", "fc.bnm"))
+    assert [l.name for l in fc.layers] == ["L1", "L2", "L3", "L4"]
+    cnn = Model.load(os.path.join(root, "tests", "golden", "models", "cnn_48.bnm"))
+    assert [l.name for l in cnn.layers] == ["L2", "L4", "L6", "L7", "L9", "L11", "L13", "L15"]
+    again = Model.from_blob(cnn.to_blob())
+    assert [l.name for l in again.layers] == [l.name for l in cnn.layers]
