@@ -16,6 +16,26 @@ e.set_option(_lib.OPT_PATH, _lib.PATH_LAYERS); a = e.infer(q)
 e.set_option(_lib.OPT_PATH, _lib.PATH_TCGEN05); b = e.infer(q)
 assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 print('layers == tcgen05 on binary160, quantised input ok')
+# both CNN front-end kernels on a 48-channel model (tiles that straddle images), emulation mode, fused gather on one GPU
+import torch, ctypes as C
+m48 = Model.load('tests/golden/models/cnn_48.bnm')
+imgs = np.random.default_rng(1).integers(-128, 128, size=(777, 256)).astype(np.int8)
+outs = []
+for fe in (_lib.CNN_CUDA_CORES, _lib.CNN_TENSOR_CORES):
+    e = E.Engine(m48); e.set_option(_lib.OPT_CNN_FRONTEND, fe); outs.append(e.infer(imgs)); e.close()
+assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+e = E.Engine(Model.load('tests/golden/models/fc.bnm'))
+lg = e.inference_quantized(x)
+n = 148 * 128 + 77
+d_img = torch.randint(-128, 128, (n, 256), dtype=torch.int8, device='cuda')
+d_log = torch.empty((n, 10), dtype=torch.int32, device='cuda'); d_lab = torch.empty(n, dtype=torch.int32, device='cuda')
+g_log = torch.zeros((n + 256, 10), dtype=torch.int32, device='cuda'); g_lab = torch.zeros(n + 256, dtype=torch.int32, device='cuda')
+g = _lib.BnmGather(); g.n_labels_dst = 1; g.n_logits_dst = 1; g.row_offset = 128
+g.labels_dst[0] = g_lab.data_ptr(); g.logits_dst[0] = g_log.data_ptr()
+_lib.check(e.lib.bnm_infer_batch_device_gather(e.handle, C.c_void_p(d_img.data_ptr()), n, C.c_void_p(d_log.data_ptr()), C.c_void_p(d_lab.data_ptr()), C.byref(g), None), 'gather')
+torch.cuda.synchronize()
+assert torch.equal(g_log[128:128 + n], d_log) and torch.equal(g_lab[128:128 + n], d_lab)
+print('cnn front-ends agree, emulation mode ran, fused gather ok')
 " > gpurun_out/sanitize_$tool.log 2>&1
   echo "exit $?"; grep -E "ERROR SUMMARY|smoke|ok$|Error|error" gpurun_out/sanitize_$tool.log | head -12
 done
