@@ -258,7 +258,9 @@ __device__ __forceinline__ void issue_layer_ts(const ChainParams &P, int l, uint
             if (leader) umma_i8_ts(d_tmem, a_tmem + k * 8, b0 + bo, idesc, bo != 0);
 }
 
-template <int kSlots, bool kTrace, bool kGather>
+// kManyClasses: more than 16 classes (chunked logits / argmax epilogue).  A template parameter, like kGather, so that the common
+// kernel stays below the 32 kB instruction cache: the gather variant at 41 kB ran 9 % slower for code size alone.
+template <int kSlots, bool kTrace, bool kGather, bool kManyClasses>
 __global__ void __launch_bounds__(kMaxWG * 160, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -428,7 +430,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                         const uint32_t ncls = P.n_classes;
                         int32_t *dst = P.logits + img * ncls;
                         uint32_t pos;
-                        if (ncls <= 16) {
+                        if (!kManyClasses) {
                             uint32_t x[16];
                             tmem_ld_x16(d_tm, x);
                             tmem_ld_wait();
@@ -454,24 +456,40 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                                     }
                                 };
                                 store_row(dst);
-                                if (kGather && !(P.off_gstage && full_tile))
+                                if (kGather && !P.off_gstage) {
+#pragma unroll 1
                                     for (uint32_t d = 0; d < P.n_log_dst; d++) store_row(P.log_dst[d] + (P.row0 + img) * ncls);   // peers, over NVLink
+                                }
                             }
-                            if (kGather && P.off_gstage && full_tile && P.n_log_dst) {
+                            if (kGather && P.off_gstage && P.n_log_dst) {
                                 // peers: this warp's 32 rows are contiguous at every destination (32 x 4 ncls bytes).  Stage them in
                                 // shared memory and push them with ONE bulk copy per destination -- full NVLink packets instead of
-                                // 8-byte stores scattered at a 4 ncls stride.
+                                // 8-byte stores scattered at a 4 ncls stride.  (Compact code on purpose: the kernel's hot loop must
+                                // keep fitting the instruction cache.)
                                 int32_t *stg = reinterpret_cast<int32_t *>(smem + P.off_gstage) + warp * 32 * ncls;
 #pragma unroll
                                 for (int j = 0; j < 16; j++)
                                     if ((uint32_t)j < ncls) stg[lane * ncls + j] = (int)x[j];
-                                fence_proxy_async_smem();
-                                __syncwarp();
-                                if (elect_one()) {
-                                    const size_t row = P.row0 + (size_t)tile * kTileM + quarter * 32;
-                                    for (uint32_t d = 0; d < P.n_log_dst; d++) bulk_store_1d(P.log_dst[d] + row * ncls, stg, 128 * ncls);
-                                    bulk_commit();
-                                    bulk_wait_read<0>();   // the staging rows may be overwritten by this warp's next tile
+                                const size_t row = P.row0 + (size_t)tile * kTileM + quarter * 32;
+                                if (full_tile) {
+                                    fence_proxy_async_smem();
+                                    __syncwarp();
+                                    if (elect_one()) {
+#pragma unroll 1
+                                        for (uint32_t d = 0; d < P.n_log_dst; d++) bulk_store_1d(P.log_dst[d] + row * ncls, stg, 128 * ncls);
+                                        bulk_commit();
+                                        bulk_wait_read<0>();   // the staging rows may be overwritten by this warp's next tile
+                                    }
+                                } else {   // ragged last tile: the valid rows, word by word (coalesced)
+                                    __syncwarp();
+                                    const size_t base_img = (size_t)tile * kTileM + quarter * 32;
+                                    const uint32_t valid = base_img < P.n ? (uint32_t)min((size_t)32, P.n - base_img) * ncls : 0;
+#pragma unroll 1
+                                    for (uint32_t d = 0; d < P.n_log_dst; d++) {
+                                        int32_t *pd = P.log_dst[d] + row * ncls;
+#pragma unroll 1
+                                        for (uint32_t idx = lane; idx < valid; idx += 32) pd[idx] = stg[idx];
+                                    }
                                 }
                                 __syncwarp();
                             }
@@ -495,11 +513,14 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 #pragma unroll
                                     for (int j = 0; j < 16; j++)
                                         if (c + j < ncls) dst[c + j] = (int)x[j];
-                                    for (uint32_t d = 0; kGather && d < P.n_log_dst; d++) {
-                                        int32_t *pd = P.log_dst[d] + (P.row0 + img) * ncls;
+                                    if (kGather) {
+#pragma unroll 1
+                                        for (uint32_t d = 0; d < P.n_log_dst; d++) {
+                                            int32_t *pd = P.log_dst[d] + (P.row0 + img) * ncls + c;
 #pragma unroll
-                                        for (int j = 0; j < 16; j++)
-                                            if (c + j < ncls) pd[c + j] = (int)x[j];
+                                            for (int j = 0; j < 16; j++)
+                                                if (c + j < ncls) pd[j] = (int)x[j];
+                                        }
                                     }
                                 }
                             }
@@ -508,6 +529,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                         }
                         if (full_tile || img < P.n) {
                             if (P.labels) P.labels[img] = pos;
+#pragma unroll 1
                             for (uint32_t d = 0; kGather && d < P.n_lab_dst; d++) {
                                 if (P.lab_u8) reinterpret_cast<uint8_t *>(P.lab_dst[d])[P.row0 + img] = (uint8_t)pos;
                                 else P.lab_dst[d][P.row0 + img] = pos;
@@ -636,12 +658,17 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     if (cudaDeviceSynchronize() != cudaSuccess) { fc_chain_plan_destroy(plan); return fail("weight image kernel failed"); }
     p.w_image = plan->d_w_image;
     p.err = plan->d_err;
-    if (cudaFuncSetAttribute(fc_chain_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(plan->smem_bytes, plan->g_smem_bytes)) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(plan->smem_bytes, plan->g_smem_bytes)) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(fc_chain_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
+    const int smem_any = (int)std::max(plan->smem_bytes, plan->g_smem_bytes);
+    if (cudaFuncSetAttribute(fc_chain_kernel<1, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
         return fail("cannot opt in to the required dynamic shared memory");
     }
@@ -723,7 +750,7 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     const CUtensorMap &tmap = *tmap_p;
     unsigned grid = (unsigned)std::min<uint32_t>(p.n_tiles, (uint32_t)plan->sm_count);
     long long *d_trace = nullptr;
-    const char *trace_path = (plan->trace_path.empty() || gather) ? nullptr : plan->trace_path.c_str();   // diagnostics build path
+    const char *trace_path = (plan->trace_path.empty() || gather || plan->p.n_classes > 16) ? nullptr : plan->trace_path.c_str();   // diagnostics build path
     if (trace_path) { cudaMalloc(&d_trace, 2048 * sizeof(long long)); cudaMemset(d_trace, 0, 2048 * sizeof(long long)); }
     p.trace = d_trace;
     // Mode 2 drops the grid-dependency wait, i.e. EVERY ordering against the work enqueued before this launch on the stream
@@ -736,8 +763,8 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     if (plan->stagger_override >= 0) p.stagger_cycles = (uint32_t)plan->stagger_override;
     plan->prev_in = in; plan->prev_logits = logits; plan->prev_labels = labels; plan->prev_stream = st; plan->prev_valid = true;
     if (trace_path) {
-        if (p.n_slots == 1) fc_chain_kernel<1, true, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
-        else fc_chain_kernel<2, true, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+        if (p.n_slots == 1) fc_chain_kernel<1, true, false, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
+        else fc_chain_kernel<2, true, false, false><<<grid, plan->threads, plan->smem_bytes, st>>>(tmap, p);
     } else {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -751,8 +778,12 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
         cfg.attrs = attr;
         cfg.numAttrs = plan->overlap ? 1 : 0;
         const bool g = p.n_lab_dst || p.n_log_dst;
-        cudaError_t e = p.n_slots == 1 ? (g ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, false>, tmap, p))
-                                       : (g ? cudaLaunchKernelEx(&cfg, fc_chain_kernel<2, false, true>, tmap, p) : cudaLaunchKernelEx(&cfg, fc_chain_kernel<2, false, false>, tmap, p));
+        const bool many = p.n_classes > 16;
+        cudaError_t e;
+#define BNM_LAUNCH(S, G, M) e = cudaLaunchKernelEx(&cfg, fc_chain_kernel<S, false, G, M>, tmap, p)
+        if (p.n_slots == 1) { if (g) { if (many) BNM_LAUNCH(1, true, true); else BNM_LAUNCH(1, true, false); } else { if (many) BNM_LAUNCH(1, false, true); else BNM_LAUNCH(1, false, false); } }
+        else { if (g) { if (many) BNM_LAUNCH(2, true, true); else BNM_LAUNCH(2, true, false); } else { if (many) BNM_LAUNCH(2, false, true); else BNM_LAUNCH(2, false, false); } }
+#undef BNM_LAUNCH
         if (e != cudaSuccess) return -4;
     }
     if (trace_path) {   // diagnostics only: synchronous dump of the phase clocks
