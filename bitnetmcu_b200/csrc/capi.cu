@@ -435,7 +435,8 @@ static int infer_device_impl(bnm_model *m, const int8_t *images, size_t n, int32
                              int8_t *slot_feat = nullptr) {
     if (!m || (n && (!images || !logits))) return fail(BNM_E_ARG, "bnm_infer_batch_device: null argument");
     if (n == 0) return 0;
-    if (((uintptr_t)images | (uintptr_t)logits) & 15) return fail(BNM_E_ARG, "device buffers must be 16-byte aligned");
+    if ((uintptr_t)images & 15) return fail(BNM_E_ARG, "the device image buffer must be 16-byte aligned (TMA)");
+    if ((uintptr_t)logits & 7) return fail(BNM_E_ARG, "the device logits buffer must be 8-byte aligned (64-bit row stores)");
     CU_TRY(cudaSetDevice(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool fused = bnm_model_active_path(m) == BNM_PATH_TCGEN05;

@@ -379,37 +379,40 @@ __global__ void __launch_bounds__(kCnnTcMaxThreads, 1) k_cnn_frontend16_tc(const
         // tiles of this warpgroup, in order: groups j = (k * gridDim + blockIdx) * n_wg + g, tiles tau = 0 .. T-1 of each
         const size_t stride = (size_t)gridDim.x * n_wg;
         size_t j = (size_t)blockIdx.x * n_wg + g;
-        uint32_t tau = 0, buf = 0;
+        uint32_t tau = 0, buf = 1;
         auto advance = [&](size_t &jj, uint32_t &tt) { if (++tt == T) { tt = 0; jj += stride; } };
-        if (j < P.n_groups) {
-            size_t first; uint32_t count;
-            unit_images(j, 0, first, count);
-            load_unit(j, 0);
-            build_unit(0, count);
-            size_t jn = j; uint32_t tn = 0;
-            advance(jn, tn);
-            if (jn < P.n_groups) load_unit(jn, tn);
-        }
-        while (j < P.n_groups) {
-            size_t first; uint32_t count;
-            unit_images(j, tau, first, count);
-            issue_piece(buf, tau, count, 0);
-            issue_piece(buf, tau, count, 1);
-            // Every MMA of the tile before this one has completed (its pieces 2 and 3 were drained before the two waits above
-            // passed): the other im2col buffer is free for the next tile.
-            size_t jn = j; uint32_t tn = tau;
-            advance(jn, tn);
-            if (jn < P.n_groups) {
-                size_t nfirst; uint32_t ncount;
-                unit_images(jn, tn, nfirst, ncount);
-                build_unit(buf ^ 1, ncount);
-                size_t j2 = jn; uint32_t t2 = tn;
-                advance(j2, t2);
-                if (j2 < P.n_groups) load_unit(j2, t2);
+        // Software pipeline over this warpgroup's tiles: while tile u is being issued (four pieces), tile u + 1 is built into the
+        // other im2col buffer and the images of tile u + 2 are fetched into registers.  The first pass has no current tile and only
+        // builds (one copy of every stage in the code: the kernel's hot instructions have to fit the 32 kB instruction cache).
+        bool cur_valid = false;
+        uint32_t count = 0;
+        size_t jn = j; uint32_t tn = 0;
+        if (jn < P.n_groups) load_unit(jn, tn);
+        while (cur_valid || jn < P.n_groups) {
+            bool built_next = false;
+#pragma unroll 1
+            for (uint32_t k = 0; k < 4; k++) {
+                if ((k == 2 || !cur_valid) && !built_next && jn < P.n_groups) {
+                    // k == 2: every MMA of the tile before the current one has completed (its pieces 2 and 3 were drained before
+                    // the waits of this tile's pieces 0 and 1 passed), so the other im2col buffer is free
+                    size_t nfirst; uint32_t ncount;
+                    unit_images(jn, tn, nfirst, ncount);
+                    build_unit(buf ^ 1, ncount);
+                    size_t j2 = jn; uint32_t t2 = tn;
+                    advance(j2, t2);
+                    if (j2 < P.n_groups) load_unit(j2, t2);
+                    built_next = true;
+                }
+                if (cur_valid) issue_piece(buf, tau, count, k);
             }
-            issue_piece(buf, tau, count, 2);
-            issue_piece(buf, tau, count, 3);
-            j = jn; tau = tn; buf ^= 1;
+            // the tile just built becomes the current one
+            cur_valid = built_next;
+            if (built_next) {
+                size_t f0;
+                unit_images(jn, tn, f0, count);
+                j = jn; tau = tn; buf ^= 1;
+                advance(jn, tn);
+            }
         }
     } else {
         // ======================= consumer warpgroup g: thread r = TMEM lane r =======================
@@ -454,20 +457,24 @@ __global__ void __launch_bounds__(kCnnTcMaxThreads, 1) k_cnn_frontend16_tc(const
         };
         load_weights(ch_one);
         size_t j_prev = 0;
-        for (size_t j = (size_t)blockIdx.x * n_wg + g; j < P.n_groups; j_prev = j, j += stride, gcount++) {
+        for (size_t j = (size_t)blockIdx.x * n_wg + g;; j_prev = j, j += stride, gcount++) {
+            const bool have = j < P.n_groups;   // one extra pass drains the last group
             int4 *raw = reinterpret_cast<int4 *>(base + P.off_raw + (g * 2 + (gcount & 1)) * P.raw_buf_bytes);
-            for (uint32_t tau = 0; tau < T; tau++, parity ^= 1) {
-                const uint32_t item = tau * 128 + r;
-                if (T > 1) load_weights(item % C);   // T == 1: the thread's channel never changes, loaded once above
-                int f[4] = {0, 0, 0, 0};
-                cnn_tile_tail<kConv3Packed>(tm, bf0, bf1, be0, be1, parity, W, f, P.err);
-                raw[item] = make_int4(f[0], f[1], f[2], f[3]);   // thread-private slot: read back only by this thread
+            if (have) {
+                for (uint32_t tau = 0; tau < T; tau++, parity ^= 1) {
+                    const uint32_t item = tau * 128 + r;
+                    if (T > 1) load_weights(item % C);   // T == 1: the thread's channel never changes, loaded once above
+                    int f[4] = {0, 0, 0, 0};
+                    cnn_tile_tail<kConv3Packed>(tm, bf0, bf1, be0, be1, parity, W, f, P.err);
+                    raw[item] = make_int4(f[0], f[1], f[2], f[3]);   // thread-private slot: read back only by this thread
+                }
             }
             // end of group gcount: (1) finish the previous group, (2) clear the maxima of the next one, (3) publish ours, (4) arrive
             if (gcount > 0) {
                 mbar_wait_a(bgrp, (gcount - 1) & 1, P.err, 14);
                 normalise_group(j_prev, gcount - 1);
             }
+            if (!have) break;
             if (r < 8) imax[((gcount + 1) % 3) * 8 + r] = 0;
             {
                 int *imx = imax + (gcount % 3) * 8;
@@ -478,10 +485,6 @@ __global__ void __launch_bounds__(kCnnTcMaxThreads, 1) k_cnn_frontend16_tc(const
                 }
             }
             mbar_arrive_a(bgrp);
-        }
-        if (gcount > 0) {
-            mbar_wait_a(bgrp, (gcount - 1) & 1, P.err, 14);
-            normalise_group(j_prev, gcount - 1);
         }
     }
     tc_fence_before();

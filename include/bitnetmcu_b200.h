@@ -136,7 +136,7 @@ BNM_API int bnm_model_active_path(const bnm_model *m);
  * through the GPU in chunks with copies overlapped and returns when the results are in `logits`/`labels`. */
 BNM_API int bnm_infer_batch(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels);
 
-/* Device version: pointers are device memory on the model's GPU (16-byte aligned); asynchronous on `stream`
+/* Device version: pointers are device memory on the model's GPU (images 16-byte, logits 8-byte aligned); asynchronous on `stream`
  * (a cudaStream_t, NULL = default stream).  No host synchronisation. */
 BNM_API int bnm_infer_batch_device(bnm_model *m, const int8_t *images, size_t n, int32_t *logits, uint32_t *labels,
                                    void *stream);
