@@ -465,6 +465,62 @@ def e2e_through_c_abi(ctx, eng, host_imgs, steps, warm=3, keep=None):
         lib.bnm_host_free(p_in); lib.bnm_host_free(p_log); lib.bnm_host_free(p_lab)
 
 
+def run_float_input(ctx, name, batch, steps, warmup, args):
+    """float32 images in (1 024 B/image), the scaling of test_inference.py:140-141 fused into the FC kernel's load
+    stage (bnm_infer_batch_device_f32) -- next to the chain of the scaling kernel and the int8 kernel it replaces.  Parity: the fused
+    launch's full batch against the chain's, and a slice against NumPy scaling + oracle."""
+    from bitnetmcu_b200 import engine as E
+    from bitnetmcu_b200.engine import Engine
+    torch = ctx.torch
+    model = load_model(name)
+    eng = Engine(model, device=ctx.local_rank)
+    n, C = batch, eng.n_classes
+    rng = np.random.default_rng(99 + ctx.rank)
+    host = rng.normal(size=(1 << 16, eng.img_bytes)).astype(np.float32)
+    d_x = [torch.from_numpy(host).to(ctx.dev).repeat(n >> 16, 1).contiguous() for _ in range(2)]
+    d_x[1].mul_(1.5)
+    d_q = torch.empty((n, eng.img_bytes), dtype=torch.int8, device=ctx.dev)
+    d_log = [torch.empty((n, C), dtype=torch.int32, device=ctx.dev) for _ in range(2)]
+    d_lab = [torch.empty(n, dtype=torch.int32, device=ctx.dev) for _ in range(2)]
+    st = ctx.stream.cuda_stream
+
+    def fused(i):
+        eng.infer_device_f32(d_x[i & 1], d_log[0], d_lab[0], st)
+
+    def chained(i):
+        E.quantize_images_device(d_x[i & 1], d_q, st)
+        eng.infer_device(d_q, d_log[1], d_lab[1], st)
+    ms_f, _ = ctx.timed_steps(fused, steps, warmup)
+    ms_c, _ = ctx.timed_steps(chained, steps, warmup)
+    fused(1); chained(1)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(d_log[0], d_log[1]) and torch.equal(d_lab[0], d_lab[1]))
+    parity = same
+    if ctx.rank == 0:
+        try:
+            from oracle.oracle import Oracle
+            x = (host[:4096] * np.float32(1.5))
+            scale = np.float32(127.0) / np.maximum(np.abs(x).max(axis=-1, keepdims=True), np.float32(1e-5))
+            q = np.round(x * scale).clip(-128, 127).astype(np.int8)
+            oo, ol = Oracle().infer(model, q, threads=checker_threads())
+            parity = bool(same and np.array_equal(d_log[0][:4096].cpu().numpy(), oo) and np.array_equal(d_lab[0][:4096].cpu().numpy().astype(np.uint32), ol))
+        except Exception as ex:
+            parity = f"oracle unavailable: {ex}"
+    peak, peak_src, _ = measured_peaks()
+    bpi = 4 * eng.img_bytes + 4 * C
+    out = {"name": name + "_float_input", "workload": f"{name}: float32 images [{n}][{eng.img_bytes}] -> int32 logits, input scaling fused into the FC kernel",
+           "value": ctx.world * n / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f, "steps": steps, "warmup": warmup, "gpu_launches_per_step": 1,
+           "value_chained_kernels": ctx.world * n / (ms_c * 1e-3), "ms_per_step_chained_kernels": ms_c,
+           "roofline": {"bound": "hbm", "achieved": bpi * n / (ms_f * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bpi * n / (ms_f * 1e-3) / 1e9 / peak,
+                        "algorithmic_bytes_per_image": bpi, "peak_source": peak_src, "traffic": None,
+                        "chained_kernels_bytes_per_image": bpi + 2 * eng.img_bytes},
+           "parity": parity, "parity_check": "fused launch == scaling kernel + int8 kernel on the full batch; first 4096 images == NumPy scaling + oracle"}
+    eng.close()
+    del d_x, d_q, d_log, d_lab
+    torch.cuda.empty_cache()
+    return out
+
+
 _TRAFFIC = None
 
 
@@ -685,6 +741,12 @@ def main():
                 configs.append(c)
             except Exception as ex:
                 configs.append({"name": name, "error": str(ex)[:300]})
+        try:
+            c = run_float_input(ctx, "fc", 1 << 20, steps=10, warmup=3, args=args)
+            log(f"config {c['name']}: fused {c['value'] / 1e9:.3f} G img/s (frac {c['roofline']['frac']:.3f}), chained {c['value_chained_kernels'] / 1e9:.3f}, parity {c['parity']}")
+            configs.append(c)
+        except Exception as ex:
+            configs.append({"name": "fc_float_input", "error": str(ex)[:300]})
 
     cpu_base = None
     latency = None

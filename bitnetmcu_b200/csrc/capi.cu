@@ -88,6 +88,8 @@ struct bnm_model {
     // test_inference.py:146-150): pinned staging buffers, one stream, one synchronisation
     int8_t *small_h_in = nullptr, *small_d_in = nullptr;     // [kSmallBatch][img_bytes]
     int32_t *small_h_out = nullptr, *small_d_out = nullptr;  // logits [n][n_classes] then labels [n]
+    int8_t *d_f32_scratch = nullptr;   // bnm_infer_batch_device_f32 fallback: quantised images
+    size_t f32_scratch_n = 0;
     int small_zero_copy = 1;   // 0: H2D + D2H copies; 1 (default, measured fastest: 14.3 vs 20.1 / 16.8 us per call): the kernel writes results
                                // straight into mapped pinned host memory; 2: ... and reads the images from it (TMA over PCIe)
 };
@@ -314,6 +316,7 @@ extern "C" void bnm_model_destroy(bnm_model *m) {
     cudaFree(m->d_err);
     cudaFree(m->small_d_in);
     cudaFree(m->small_d_out);
+    cudaFree(m->d_f32_scratch);
     if (m->small_h_in) cudaFreeHost(m->small_h_in);
     if (m->small_h_out) cudaFreeHost(m->small_h_out);
     for (auto &s : m->slots) {
@@ -755,6 +758,30 @@ extern "C" int bnm_quantize_images_device(const float *images, size_t n, uint32_
     launch_quantize_images(images, elems, out, n, static_cast<cudaStream_t>(stream));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail(BNM_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+}
+
+// float images -> logits / labels on the device.  FC models on the fused path (rows of <= 256 elements, <= 16 classes): ONE kernel, the
+// input scaling fused into its load stage.  Everything else: the scaling kernel into a scratch buffer, then the ordinary path.
+extern "C" int bnm_infer_batch_device_f32(bnm_model *m, const float *images, size_t n, int32_t *logits, uint32_t *labels, void *stream) {
+    if (!m || (n && (!images || !logits))) return fail(BNM_E_ARG, "bnm_infer_batch_device_f32: null argument");
+    if (n == 0) return 0;
+    if ((uintptr_t)images & 15) return fail(BNM_E_ARG, "the device image buffer must be 16-byte aligned");
+    if ((uintptr_t)logits & 7) return fail(BNM_E_ARG, "the device logits buffer must be 8-byte aligned (64-bit row stores)");
+    CU_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool fused_fc = bnm_model_active_path(m) == BNM_PATH_TCGEN05 && m->model_class == BNM_MODEL_FCMNIST;
+    if (fused_fc && fc_chain_float_input_supported(m->plan)) {
+        int rc = fc_chain_launch_f32(m->plan, images, n, logits, labels, st);
+        return rc ? fail(BNM_E_CUDA, "fused float-input kernel launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())) : 0;
+    }
+    if (m->f32_scratch_n < n) {
+        cudaFree(m->d_f32_scratch);
+        m->d_f32_scratch = nullptr; m->f32_scratch_n = 0;
+        CU_TRY(cudaMalloc(&m->d_f32_scratch, n * (size_t)m->img_bytes));
+        m->f32_scratch_n = n;
+    }
+    launch_quantize_images(images, m->img_bytes, m->d_f32_scratch, n, st);
+    return bnm_infer_batch_device(m, m->d_f32_scratch, n, logits, labels, stream);
 }
 
 extern "C" int bnm_quantize_images(const float *images, size_t n, uint32_t elems, int8_t *out) {

@@ -27,6 +27,10 @@ namespace bnm {
 
 constexpr int kMaxWG = 3;        // epilogue warpgroups; with 2 slots each: 6 x (64 D + 16 A) = 480 of the 512 TMEM columns
 constexpr int kMaxStages = 8;
+constexpr uint32_t kFloatQuantWarps = 8;    // float-input path: quantiser warps per CTA
+constexpr uint32_t kFloatWG = 2;            // ... next to two epilogue warpgroups (four tiles in flight are plenty at 1 kB per image): 576 threads
+constexpr uint32_t kFloatRowsPerWarp = 128 / kFloatQuantWarps;   // rows of every tile per quantiser warp
+constexpr uint32_t kFloatGroupRows = 4;     // rows per bulk copy of a quantiser warp (4 kB for 256-element rows) = rows per pass
 
 struct ChainParams {
     int n_layers;
@@ -61,6 +65,9 @@ struct ChainParams {
     int32_t *log_dst[kMaxGatherDst];
     size_t row0;
     uint32_t lab_u8;                  // gather launches: lab_dst are uint8 buffers (one byte per label)
+    const float *fimages;             // float-input launches (fc_chain_kernel<..., kFloatIn>): float32 [n][in_elems] instead of the int8 tensor map
+    uint32_t in_elems;                // real elements per image row (<= 256 for the float path)
+    uint32_t off_fring;               // float-input launches: smem offset of the quantiser warps' float rings (8 warps x 2 slots x 4 kB)
     uint32_t off_gstage;              // gather launches: smem offset of the per-warp staging rows for the bulk peer stores (0: none)
 };
 
@@ -78,6 +85,9 @@ struct FcChainPlan {
     // one bulk copy per destination (full NVLink packets instead of 8-byte scattered stores): their own ring depth and layout
     uint32_t g_n_stages = 0, g_off_w = 0, g_off_gstage = 0;
     size_t g_smem_bytes = 0;
+    // float-input launches: fewer int8 stages, the freed shared memory holds the quantiser warps' float rings
+    uint32_t f_n_stages = 0, f_off_w = 0, f_off_fring = 0;
+    size_t f_smem_bytes = 0;
     // launch-path state (nothing on the launch path reads the environment or re-encodes a known tensor map)
     struct TmapSlot { const void *ptr = nullptr; size_t n = 0; CUtensorMap map; };
     TmapSlot tmaps[4];                // tensor maps of the most recent (pointer, n) pairs: double/triple-buffered callers hit every time
@@ -260,13 +270,20 @@ __device__ __forceinline__ void issue_layer_ts(const ChainParams &P, int l, uint
 
 // kManyClasses: more than 16 classes (chunked logits / argmax epilogue).  A template parameter, like kGather, so that the common
 // kernel stays below the 32 kB instruction cache: the gather variant at 41 kB ran 9 % slower for code size alone.
-template <int kSlots, bool kTrace, bool kGather, bool kManyClasses>
-__global__ void __launch_bounds__(kMaxWG * 160, 1)
+// kFloatIn: the input scaling of the reference's caller (test_inference.py:140-141: scale = 127 / max(max|x|, 1e-5), q = round-half-even
+// (x * scale) clipped to int8, all float32) is fused into the load stage: eight extra warps fetch float32 rows from HBM (1 kB per
+// image, bulk async copies into a small ring), reduce each row's absolute maximum, quantise and write the int8 row
+// straight into the shared-memory image stage in the SWIZZLE_128B layout the layer-1 MMA expects -- the place of the TMA load.
+// Float input then costs 1 024 B of HBM traffic per image once, instead of 1 024 + 256 (quantise kernel) + 256 (this kernel).
+template <int kSlots, bool kTrace, bool kGather, bool kManyClasses, bool kFloatIn = false>
+__global__ void __launch_bounds__(kFloatIn ? kFloatWG * 160 + 32 * kFloatQuantWarps : kMaxWG * 160, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[2][kMaxStages], bar_mma[kMaxWG][kMaxSlots], bar_ready[kMaxWG][kMaxSlots];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bar_w;   // weight image landed (one bulk async copy, no generic-proxy writes)
+    __shared__ __align__(8) uint64_t bar_fload[kFloatQuantWarps][2];   // kFloatIn: a quantiser warp's ring slot has landed (bulk async copy)
+    __shared__ __align__(8) uint64_t bar_free[kMaxStages];   // kFloatIn: the layer-1 MMAs of a stage's tile are done, the quantiser warps may refill it
 
     const long long t_entry = clock64();
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -316,10 +333,12 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     const bool setup_thread = tid == n_wg * 128;
     if (warp == n_wg * 4) {
         // barrier init, one lane per barrier (29 mbarrier.init in a row by one thread took ~1100 cycles of every launch)
-        if (lane < 2 * kMaxStages) { if ((lane % kMaxStages) < n_st) mbar_init(&bar_full[lane / kMaxStages][lane % kMaxStages], 1); }
+        if (lane < 2 * kMaxStages) { if ((lane % kMaxStages) < n_st) mbar_init(&bar_full[lane / kMaxStages][lane % kMaxStages], kFloatIn ? kFloatQuantWarps : 1); }
         else if (lane < 2 * kMaxStages + kMaxWG * kMaxSlots) mbar_init(&bar_mma[0][0] + (lane - 2 * kMaxStages), 1);
         else if (lane < 2 * kMaxStages + 2 * kMaxWG * kMaxSlots) mbar_init(&bar_ready[0][0] + (lane - 2 * kMaxStages - kMaxWG * kMaxSlots), kReadyArrivals);
         else if (lane == 2 * kMaxStages + 2 * kMaxWG * kMaxSlots) mbar_init(&bar_w, 1);
+        if (kFloatIn && lane < n_st) mbar_init(&bar_free[lane], 1);
+        if (kFloatIn && lane >= 8 && lane < 8 + 2 * kFloatQuantWarps) mbar_init(&bar_fload[(lane - 8) >> 1][lane & 1], 1);
         fence_mbar_init();
         __syncwarp();
     }
@@ -336,7 +355,8 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         // that one has completed and flushed (no-op without a programmatic dependency).  Every other access of this CTA
         // happens after a barrier that these loads complete, i.e. after this wait.
         if (P.wait_prior_grid) asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
+        if (!kFloatIn)
+            for (uint32_t i = 0; i < n_st && i < my_tiles; i++) issue_tile_load(i);
         if (kTrace && P.trace && blockIdx.x == 0) P.trace[1017] = clock64();   // first loads issued
     } else if (warp == 1) {
         tmem_alloc<512>(&tmem_base_s);
@@ -412,7 +432,10 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                     tc_fence_after();
                     BNM_TRACE_POINT();   // MMAs of layer l+1 complete
                     if (l + 1 < n_layers) {
-                        if (l == 0 && quarter == 1 && i + n_st < my_tiles && elect_one()) issue_tile_load(i + n_st);   // stage is free
+                        if (l == 0 && quarter == 1 && i + n_st < my_tiles && elect_one()) {   // stage is free
+                            if (kFloatIn) mbar_arrive(&bar_free[i % n_st]);
+                            else issue_tile_load(i + n_st);
+                        }
                         if (n_pad_l == 64) relunorm_tmem64(d_tm, d_tm + a_off);
                         else relunorm_tmem(d_tm, d_tm + a_off, n_pad_l);
                         // this thread's reads of D and writes of A are complete: tell the issuer (128 fire-and-forget arrivals per
@@ -541,6 +564,82 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
             }
     }
 
+    if (kFloatIn && warp >= n_wg * 5) {
+        // ======================= quantiser warps (float input): warp qw converts rows 16 qw .. 16 qw + 15 of every tile =======================
+        // The float rows of a warp's share are contiguous in HBM: they are fetched four rows (4 kB) at a time by one bulk async copy
+        // into the warp's own two-slot ring (64 kB in flight per SM: enough to cover the HBM latency).  A pass converts four rows at
+        // once, eight lanes per row: a lane holds 32 of its row's floats (eight float4, visited in an order rotated by the row so that
+        // the four rows never meet in a bank), so the row maximum needs three shuffles and every lane has 32 independent elements to
+        // scale, round and pack.  The int8 words go straight into the image stage the layer-1 MMA reads.
+        const uint32_t qw = warp - n_wg * 5;
+        const uint32_t elems = P.in_elems, n_f4 = elems >> 2, row_words = P.in_atoms * 32;   // float4 per float row, 4-byte words per int8 row
+        const float *src = P.fimages;
+        uint8_t *ring = smem + P.off_fring + qw * (2 * kFloatGroupRows * 1024);
+        uint64_t *fbar = &bar_fload[qw][0];
+        constexpr uint32_t kGroupsPerTile = kFloatRowsPerWarp / kFloatGroupRows;
+        const uint32_t n_groups = my_tiles * kGroupsPerTile;   // groups of rows of this warp, in order
+        auto group_rows = [&](uint32_t gi, size_t &row) {   // first global row and number of valid rows of group gi
+            const uint32_t i = gi / kGroupsPerTile, k = gi % kGroupsPerTile;
+            row = (size_t)(tile0 + i * tile_step) * kTileM + qw * kFloatRowsPerWarp + k * kFloatGroupRows;
+            return row < P.n ? (uint32_t)min((size_t)kFloatGroupRows, P.n - row) : 0u;
+        };
+        auto issue_group = [&](uint32_t gi) {
+            size_t row;
+            const uint32_t valid = group_rows(gi, row);
+            if (lane == 0 && valid) {
+                mbar_arrive_expect_tx(&fbar[gi & 1], valid * elems * 4);
+                bulk_load_1d(ring + (gi & 1) * (kFloatGroupRows * 1024), src + row * elems, valid * elems * 4, &fbar[gi & 1]);
+            }
+        };
+        const uint32_t u = lane >> 3, sub = lane & 7;   // row of the pass, position inside the row's eight-lane team
+        uint32_t fphase = 0;   // one phase bit per ring slot
+        if (n_groups > 0) issue_group(0);
+        if (n_groups > 1) issue_group(1);
+        for (uint32_t gi = 0; gi < n_groups; gi++) {
+            const uint32_t i = gi / kGroupsPerTile, k = gi % kGroupsPerTile, s = i % n_st;
+            if (k == 0 && i >= n_st) mbar_wait(&bar_free[s], ((i / n_st) - 1) & 1, P.err, 8);   // the tile that used this stage is through layer 1
+            uint8_t *stage = smem + s * P.stage_bytes;
+            size_t row;
+            const uint32_t valid = group_rows(gi, row);
+            const uint32_t slot = gi & 1;
+            if (valid) {
+                mbar_wait(&fbar[slot], (fphase >> slot) & 1, P.err, 9);
+                fphase ^= 1u << slot;
+            }
+            const float4 *fr = reinterpret_cast<const float4 *>(ring + slot * (kFloatGroupRows * 1024)) + u * n_f4;
+            const uint32_t r = qw * kFloatRowsPerWarp + k * kFloatGroupRows + u;   // this lane's row inside the tile
+            float4 v[8];
+            float m = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t c = sub + 8 * ((j + u) & 7);
+                v[j] = (u < valid && c < n_f4) ? fr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+            }
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            // test_inference.py:140-141 / BitNetMCU.py:435-436, every step one correctly rounded float32 operation
+            const float scale = __fdiv_rn(127.0f, fmaxf(m, 1e-5f));
+            auto q = [&](float x) { int d; asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(d) : "f"(__fmul_rn(x, scale))); return (uint32_t)d; };   // round half to even, clip to int8
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t c = sub + 8 * ((j + u) & 7);   // word c of the int8 row (bytes 4c .. 4c+3)
+                const uint32_t w = __byte_perm(__byte_perm(q(v[j].x), q(v[j].y), 0x0040), __byte_perm(q(v[j].z), q(v[j].w), 0x0040), 0x5410);
+                // SWIZZLE_128B: 16-byte chunk jc of row r sits at chunk position jc ^ (r & 7) of the row's 128 bytes in its atom
+                if (c < row_words)
+                    *reinterpret_cast<uint32_t *>(stage + (c >> 5) * 16384 + r * 128 + ((((c & 31) >> 2) ^ (r & 7)) << 4) + (c & 3) * 4) = w;
+            }
+            __syncwarp();   // every lane has read its floats of this slot
+            if (gi + 2 < n_groups) issue_group(gi + 2);
+            if (k == kGroupsPerTile - 1) {
+                fence_proxy_async_smem();   // the layer-1 MMAs (async proxy) read what these generic-proxy stores wrote
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[(i / n_st) & 1][s]);
+            }
+        }
+    }
+
     tc_fence_before();
     __syncthreads();
     if (kTrace && P.trace && blockIdx.x == 0 && tid == 0) P.trace[1022] = clock64();   // all roles done
@@ -622,6 +721,16 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     // TMEM do not enforce it (launch_dependents fires before tmem_alloc blocks), shared memory does once a CTA asks for more than
     // half of the SM's 227 kB.
     plan->smem_bytes = std::max<size_t>(plan->smem_bytes, 116 * 1024);
+    if (in_bytes <= 256 && p.n_classes <= 16) {   // float-input path
+        const uint32_t fring = kFloatQuantWarps * 2 * kFloatGroupRows * 1024;
+        const uint32_t fixed_f = round_up(p.w_bytes, 128) + fring;
+        if (fixed_f + 2 * p.stage_bytes <= smem_limit) {
+            plan->f_n_stages = std::min<uint32_t>(4, (smem_limit - fixed_f) / p.stage_bytes);
+            plan->f_off_w = plan->f_n_stages * p.stage_bytes;
+            plan->f_off_fring = plan->f_off_w + round_up(p.w_bytes, 128);
+            plan->f_smem_bytes = std::max<size_t>((size_t)plan->f_off_fring + fring + 1024, 116 * 1024);
+        }
+    }
     if (p.n_classes <= 16) {   // staged peer stores: 12 warps x 32 rows x 4 n_classes bytes next to the weights
         const uint32_t gstage = kMaxWG * 4 * 128 * p.n_classes;
         const uint32_t fixed_g = round_up(p.w_bytes, 128) + round_up(gstage, 128);
@@ -658,7 +767,7 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     if (cudaDeviceSynchronize() != cudaSuccess) { fc_chain_plan_destroy(plan); return fail("weight image kernel failed"); }
     p.w_image = plan->d_w_image;
     p.err = plan->d_err;
-    const int smem_any = (int)std::max(plan->smem_bytes, plan->g_smem_bytes);
+    const int smem_any = (int)std::max(std::max(plan->smem_bytes, plan->g_smem_bytes), plan->f_smem_bytes);
     if (cudaFuncSetAttribute(fc_chain_kernel<1, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<2, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
@@ -667,6 +776,8 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
         cudaFuncSetAttribute(fc_chain_kernel<2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<2, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<2, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
@@ -807,6 +918,43 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
             fclose(f);
         }
     }
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+bool fc_chain_float_input_supported(const FcChainPlan *plan) {
+    return plan && plan->f_smem_bytes != 0 && plan->in_bytes % 16 == 0;
+}
+
+// float32 images [n][in_bytes elements] -> logits / labels, the input scaling fused into the load stage (kFloatIn)
+int fc_chain_launch_f32(FcChainPlan *plan, const float *in, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st) {
+    if (n == 0) return 0;
+    if (n > 0x7fffff00ull) return -2;
+    if (!fc_chain_float_input_supported(plan)) return -6;
+    ChainParams p = plan->p;
+    p.logits = logits;
+    p.labels = labels;
+    p.n = n;
+    p.n_lab_dst = p.n_log_dst = 0;
+    p.row0 = 0;
+    p.lab_u8 = 0;
+    p.off_gstage = 0;
+    p.fimages = in;
+    p.in_elems = plan->in_bytes;
+    p.n_wg = std::min<uint32_t>(p.n_wg, kFloatWG);
+    p.n_stages = plan->f_n_stages;
+    p.off_w = plan->f_off_w;
+    p.off_fring = plan->f_off_fring;
+    p.n_tiles = (uint32_t)((n + kTileM - 1) / kTileM);
+    p.trace = nullptr;
+    p.wait_prior_grid = 1;
+    p.early_trigger = 0;
+    CUtensorMap tmap;   // not used by the float-input kernel (no TMA image loads)
+    memset(&tmap, 0, sizeof(tmap));
+    const unsigned grid = (unsigned)std::min<uint32_t>(p.n_tiles, (uint32_t)plan->sm_count);
+    const unsigned threads = p.n_wg * 160 + 32 * kFloatQuantWarps;   // epilogue + issuer warps + the quantiser warps
+    if (p.n_slots == 1) fc_chain_kernel<1, false, false, false, true><<<grid, threads, plan->f_smem_bytes, st>>>(tmap, p);
+    else fc_chain_kernel<2, false, false, false, true><<<grid, threads, plan->f_smem_bytes, st>>>(tmap, p);
+    plan->prev_valid = false;
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -84,4 +84,9 @@ void fc_chain_plan_set_overlap(FcChainPlan *p, int mode);
 int fc_chain_launch(FcChainPlan *p, const int8_t *in, size_t n, int32_t *logits, uint32_t *labels, const GatherDst *gather,
                     cudaStream_t st);
 
+// float32 images [n][in_bytes] (elements) -> logits / labels with the input scaling of test_inference.py:140-141 fused into the
+// kernel's load stage; supported for image rows of up to 256 elements and up to 16 classes
+bool fc_chain_float_input_supported(const FcChainPlan *p);
+int fc_chain_launch_f32(FcChainPlan *p, const float *in, size_t n, int32_t *logits, uint32_t *labels, cudaStream_t st);
+
 }  // namespace bnm

@@ -113,6 +113,19 @@ class Engine:
         _lib.check(self.lib.bnm_emulate_inference_quantized(self.handle, _ptr(x), x.shape[0], _ptr(out)), "bnm_emulate_inference_quantized")
         return out
 
+    def infer_device_f32(self, images, logits, labels=None, stream: Optional[int] = None) -> None:
+        """images: torch.float32 [n, img_bytes] on this GPU (un-normalised pixels, as test_inference.py:140 sees them) -> logits
+        torch.int32 [n, n_classes], labels [n].  FC models: one kernel with the input scaling fused into its load stage."""
+        import torch
+        n = images.shape[0]
+        if stream is None:
+            stream = torch.cuda.current_stream(images.device).cuda_stream
+        assert images.is_contiguous() and images.dtype == torch.float32 and images.shape[1] == self.img_bytes
+        assert logits.is_contiguous() and logits.dtype == torch.int32 and tuple(logits.shape) == (n, self.n_classes)
+        lab_ptr = C.c_void_p(labels.data_ptr()) if labels is not None else None
+        _lib.check(self.lib.bnm_infer_batch_device_f32(self.handle, C.c_void_p(images.data_ptr()), n, C.c_void_p(logits.data_ptr()), lab_ptr,
+                                                       C.c_void_p(stream)), "bnm_infer_batch_device_f32")
+
     def infer_tensor(self, images):
         """images: torch.int8 [n, img_bytes] on this engine's GPU -> (logits torch.int32 [n, n_classes], labels torch.int32 [n]) on
         the same GPU, asynchronous on torch's current stream (device memory end to end; plumbing for ``dist.sharded_infer``)."""

@@ -193,6 +193,11 @@ BNM_API int bnm_maxpool22_batch(const int32_t *activations, uint32_t xy_input, i
  *        scale = 127 / max(max|x|, 1e-5);  q = round_half_even(x * scale) clipped to [-128, 127]      (all float32)
  *    images float32 [n][elems] -> int8 [n][elems]; bit-identical to the NumPy expression.
  * ------------------------------------------------------------------------------------------- */
+/* Float images straight to logits / labels (device buffers, asynchronous on `stream`): for FC models on the fused path (image rows of
+ * <= 256 elements, <= 16 classes) this is ONE kernel -- four extra warps read the float rows, reduce the row maximum, quantise and write
+ * the int8 rows into the shared-memory stage the tensor core reads, so a float image costs 1 024 B of HBM traffic once.  Other models:
+ * the scaling kernel into a scratch buffer, then bnm_infer_batch_device.  Results are those of bnm_quantize_images + bnm_infer_batch. */
+BNM_API int bnm_infer_batch_device_f32(bnm_model *m, const float *images, size_t n, int32_t *logits, uint32_t *labels, void *stream);
 BNM_API int bnm_quantize_images(const float *images, size_t n, uint32_t elems, int8_t *out);                       /* host buffers */
 BNM_API int bnm_quantize_images_device(const float *images, size_t n, uint32_t elems, int8_t *out, void *stream);  /* device buffers */
 

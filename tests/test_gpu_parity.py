@@ -632,3 +632,67 @@ def test_fused_gather_epilogue_peer_gpu(lib, oracle):
     if lib.bnm_device_count() < 2:
         pytest.skip("needs two GPUs")
     _gather_case(lib, oracle, "fc", 148 * 128 * 3 + 5, 1)
+
+
+# ---- float input fused into the FC kernel's load stage ----------------------------------------------------------
+
+def _float_images(n, elems, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n, elems)).astype(np.float32)
+    k = min(n, 50)
+    x[:k] = (rng.integers(0, 256, size=(k, elems)) / 255.0 - 0.1307).astype(np.float32) / np.float32(0.3081)   # MNIST-like normalisation
+    if n > 60:
+        x[50] = 0.0                                                                      # all-zero image: the 1e-5 floor
+        x[51] = 1e-7
+        x[52, :] = np.float32(0.5) / np.float32(127.0) * np.arange(elems, dtype=np.float32)   # many exact .5 ties
+        x[53] = -x[52]
+        x[54, 0] = 3e38
+        x[55] = -1.0
+    return x
+
+
+@pytest.mark.parametrize("name,n", [("fc", 148 * 128 * 2 + 77), ("fc", 1), ("fc", 129), ("ternary64", 5000), ("1k", 4097), ("binary160", 3000), ("cnn_48", 2500)])
+def test_float_input_fused_into_the_fc_kernel(lib, oracle, name, n):
+    """bnm_infer_batch_device_f32: float32 images -> int32 logits in one kernel for FC models (four quantiser warps write the int8 A
+    operand of layer 1 into shared memory, SWIZZLE_128B by hand), through the scaling kernel for CNN models; compared with the
+    NumPy scaling of test_inference.py:140-141 followed by the oracle.  Tolerance 0."""
+    import torch
+    m = load_model(name)
+    x = _float_images(n, m.img_bytes, seed=n)
+    scale = np.float32(127.0) / np.maximum(np.abs(x).max(axis=-1, keepdims=True), np.float32(1e-5))
+    q = np.round(x * scale).clip(-128, 127).astype(np.int8)
+    want, want_lab = oracle.infer(m, q)
+    e = _engine(name, 0)
+    d_x = torch.from_numpy(x).cuda()
+    d_log = torch.empty((n, m.n_classes), dtype=torch.int32, device="cuda")
+    d_lab = torch.empty(n, dtype=torch.int32, device="cuda")
+    for _ in range(2):                      # twice: the stage ring wraps and the launch is repeatable
+        e.infer_device_f32(d_x, d_log, d_lab)
+    torch.cuda.synchronize()
+    got = d_log.cpu().numpy()
+    assert np.array_equal(got, want), (name, n, np.argwhere(got != want)[:5])
+    assert np.array_equal(d_lab.cpu().numpy().astype(np.uint32), want_lab)
+    e.close()
+
+
+def test_float_input_odd_row_widths(lib, oracle):
+    """Rows narrower than 256 elements (160: the second 128-byte atom is half padding; 64, 32: one atom) through the fused float path."""
+    import torch
+    from bitnetmcu_b200 import _lib, pack as P
+    from bitnetmcu_b200.engine import Engine
+    for n_in, n_out in [(160, 160), (64, 10), (32, 1), (128, 16)]:
+        m = P.random_fc_model(4, (n_in, 64, n_out), seed=n_in)
+        m.img_bytes = n_in
+        x = _float_images(1777, n_in, seed=n_in)
+        scale = np.float32(127.0) / np.maximum(np.abs(x).max(axis=-1, keepdims=True), np.float32(1e-5))
+        q = np.round(x * scale).clip(-128, 127).astype(np.int8)
+        want, want_lab = oracle.infer(m, q)
+        e = Engine(m, path=_lib.PATH_TCGEN05)
+        d_x = torch.from_numpy(x).cuda()
+        d_log = torch.empty((1777, n_out), dtype=torch.int32, device="cuda")
+        d_lab = torch.empty(1777, dtype=torch.int32, device="cuda")
+        e.infer_device_f32(d_x, d_log, d_lab)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_log.cpu().numpy(), want), (n_in, n_out)
+        assert np.array_equal(d_lab.cpu().numpy().astype(np.uint32), want_lab)
+        e.close()
