@@ -400,7 +400,7 @@ def run_config(ctx, name, batch, steps, warmup, args, check_parity=True, host_im
         peak_ops = int_alu_peak_ops(sm_max)
         roof = {"bound": "int_alu", "achieved": ops / 1e12, "peak": peak_ops / 1e12, "unit": "Top/s", "frac": ops / peak_ops,
                 "peak_source": f"IDP.4A issue rate (1 warp instruction / 2 cycles / SM sub-partition, tools/alu_rates.cu) x 148 SMs x {sm_max:.0f} MHz",
-                "macs_per_image": model.macs_per_image, "hbm_frac": hbm_ach / peak_gbs, "traffic": None}
+                "macs_per_image": model.macs_per_image, "hbm_frac": hbm_ach / peak_gbs, "traffic": traffic_for(name, n)}
     else:
         roof = {"bound": "hbm", "achieved": hbm_ach, "peak": peak_gbs, "unit": "GB/s", "frac": hbm_ach / peak_gbs,
                 "peak_source": peak_src, "algorithmic_bytes_per_image": bytes_per_image, "traffic": traffic_for(name, n),
