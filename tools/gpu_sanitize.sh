@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer passes over the smoke workload (fused FC kernel + CNN front-end, 1013 images each) and the option paths
 mkdir -p gpurun_out
-for tool in memcheck synccheck; do
+for tool in memcheck synccheck racecheck; do
   echo "== compute-sanitizer --tool $tool"
   timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 5 python -c "
 import __graft_entry__ as g
@@ -36,6 +36,15 @@ _lib.check(e.lib.bnm_infer_batch_device_gather(e.handle, C.c_void_p(d_img.data_p
 torch.cuda.synchronize()
 assert torch.equal(g_log[128:128 + n], d_log) and torch.equal(g_lab[128:128 + n], d_lab)
 print('cnn front-ends agree, emulation mode ran, fused gather ok')
+# float32 images in, scaling fused into the FC kernel's load stage (quantiser warps write the swizzled int8 stage by hand)
+nf = 148 * 128 * 2 + 53
+xf = torch.randn((nf, 256), dtype=torch.float32, device='cuda') * 3
+f_log = torch.empty((nf, 10), dtype=torch.int32, device='cuda'); f_lab = torch.empty(nf, dtype=torch.int32, device='cuda')
+e.infer_device_f32(xf, f_log, f_lab)
+torch.cuda.synchronize()
+ref = e.infer(E.quantize_images(xf.cpu().numpy()))
+assert np.array_equal(f_log.cpu().numpy(), ref[0])
+print('fused float input ok')
 " > gpurun_out/sanitize_$tool.log 2>&1
   echo "exit $?"; grep -E "ERROR SUMMARY|smoke|ok$|Error|error" gpurun_out/sanitize_$tool.log | head -12
 done
