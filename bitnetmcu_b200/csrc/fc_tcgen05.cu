@@ -25,8 +25,10 @@
 
 namespace bnm {
 
-constexpr int kMaxWG = 3;        // epilogue warpgroups; with 2 slots each: 6 x (64 D + 16 A) = 480 of the 512 TMEM columns
-constexpr int kMaxStages = 8;
+constexpr int kMaxWG = 4;        // epilogue warpgroups: three with 2 tile slots each (6 x (64 D + 16 A) = 480 of the 512 TMEM columns),
+                                 // or four with one slot each when only 4..5 slots fit (kFourWG instantiations)
+constexpr int kMaxWG2 = 3;       // ... of the two-slot form
+constexpr int kMaxStages = 7;    // (2 x kMaxStages + 2 x kMaxWG x kMaxSlots + 1 barriers are initialised by one lane each)
 constexpr uint32_t kFloatQuantWarps = 8;    // float-input path: quantiser warps per CTA
 constexpr uint32_t kFloatWG = 2;            // ... next to two epilogue warpgroups (four tiles in flight are plenty at 1 kB per image): 576 threads
 constexpr uint32_t kFloatRowsPerWarp = 128 / kFloatQuantWarps;   // rows of every tile per quantiser warp
@@ -74,7 +76,8 @@ struct ChainParams {
 struct FcChainPlan {
     ChainParams p{};
     uint8_t *d_w_image = nullptr;
-    int *d_err = nullptr;
+    int *d_err = nullptr;             // error word of the bounded device-side waits: mapped pinned host memory, readable after a trap
+    int *h_err = nullptr;
     size_t smem_bytes = 0;
     uint32_t in_bytes = 0;
     int threads = 0;
@@ -275,8 +278,8 @@ __device__ __forceinline__ void issue_layer_ts(const ChainParams &P, int l, uint
 // image, bulk async copies into a small ring), reduce each row's absolute maximum, quantise and write the int8 row
 // straight into the shared-memory image stage in the SWIZZLE_128B layout the layer-1 MMA expects -- the place of the TMA load.
 // Float input then costs 1 024 B of HBM traffic per image once, instead of 1 024 + 256 (quantise kernel) + 256 (this kernel).
-template <int kSlots, bool kTrace, bool kGather, bool kManyClasses, bool kFloatIn = false>
-__global__ void __launch_bounds__(kFloatIn ? kFloatWG * 160 + 32 * kFloatQuantWarps : kMaxWG * 160, 1)
+template <int kSlots, bool kTrace, bool kGather, bool kManyClasses, bool kFloatIn = false, bool kFourWG = false>
+__global__ void __launch_bounds__(kFloatIn ? kFloatWG * 160 + 32 * kFloatQuantWarps : (kFourWG ? kMaxWG : kMaxWG2) * 160, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[2][kMaxStages], bar_mma[kMaxWG][kMaxSlots], bar_ready[kMaxWG][kMaxSlots];
@@ -701,13 +704,18 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     p.tmem_a_off = round_up(d_cols, 32);
     p.tmem_wg_cols = p.tmem_a_off + round_up(std::max(a_cols, 1u), 16);
     if (p.tmem_wg_cols > 512) { delete plan; return fail("fused path: model does not fit the 512 TMEM columns"); }
-    {   // tiles in flight per CTA = n_wg warpgroups x n_slots slots, bounded by the 512 TMEM columns
+    {   // Tiles in flight per CTA = n_wg warpgroups x n_slots slots, bounded by the 512 TMEM columns.  Measured on B200, us per
+        // 2^20 images, warpgroups x slots: 4bitsym-64 2x1 93, 2x2 73.5, 3x1 72.2, 3x2 62.5, 4x1 63.6, four warpgroups with six slots
+        // 64.0; 2bitsym-96 (four slots fit) 2x2 98.7, three warpgroups with four slots 95.7, 4x1 81.3.  Epilogue warps matter
+        // more than slots until three warpgroups have two slots each; a fourth warpgroup then buys nothing.
         const uint32_t fit = 512 / p.tmem_wg_cols;
-        p.n_wg = std::min<uint32_t>(kMaxWG, fit);
-        p.n_slots = std::min<uint32_t>(kMaxSlots, fit / p.n_wg);
-        if (fit >= 4 && fit < 6) { p.n_wg = 2; p.n_slots = 2; }
-        if (const char *e = getenv("BNM_WG")) p.n_wg = std::max(1, std::min<int>((int)p.n_wg, atoi(e)));          // tuning knobs
-        if (const char *e = getenv("BNM_SLOTS")) p.n_slots = std::max(1, std::min<int>((int)std::min<uint32_t>(kMaxSlots, fit / p.n_wg), atoi(e)));
+        if (fit >= 6) { p.n_wg = 3; p.n_slots = 2; }
+        else { p.n_wg = std::min<uint32_t>(kMaxWG, fit); p.n_slots = 1; }
+        if (const char *e = getenv("BNM_WG")) {                                                                   // tuning knobs
+            p.n_wg = std::max(1, std::min<int>((int)std::min<uint32_t>(kMaxWG, fit), atoi(e)));
+            p.n_slots = p.n_wg <= kMaxWG2 ? std::min<uint32_t>(kMaxSlots, fit / p.n_wg) : 1;
+        }
+        if (const char *e = getenv("BNM_SLOTS")) p.n_slots = p.n_wg <= kMaxWG2 ? std::max(1, std::min<int>((int)std::min<uint32_t>(kMaxSlots, fit / p.n_wg), atoi(e))) : 1;
     }
     const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*static*/;
     p.off_w = 0;  // set below: stages first (1024-aligned), then weights
@@ -750,12 +758,13 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     plan->device = device;
 
     // weight image
-    if (cudaMalloc(&plan->d_w_image, p.w_bytes) != cudaSuccess || cudaMalloc(&plan->d_err, sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc(&plan->d_w_image, p.w_bytes) != cudaSuccess || cudaHostAlloc(&plan->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&plan->d_err, plan->h_err, 0) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
         return fail("cudaMalloc failed (weight image)");
     }
     cudaMemset(plan->d_w_image, 0, p.w_bytes);
-    cudaMemset(plan->d_err, 0, sizeof(int));
+    *plan->h_err = 0;
     for (int l = 0; l < n_layers; l++) {
         const FcLayerDev &L = layers[l];
         for (uint32_t pl = 0; pl < p.planes[l]; pl++) {
@@ -778,6 +787,10 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
         cudaFuncSetAttribute(fc_chain_kernel<2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<2, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<2, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
@@ -800,7 +813,10 @@ void fc_chain_plan_set_overlap(FcChainPlan *p, int mode) {
 void fc_chain_plan_destroy(FcChainPlan *p) {
     if (!p) return;
     if (p->d_w_image) cudaFree(p->d_w_image);
-    if (p->d_err) cudaFree(p->d_err);
+    if (p->h_err) {
+        if (*p->h_err) fprintf(stderr, "bitnetmcu_b200: fused FC kernel: bounded wait %d timed out (device trap)\n", *p->h_err);
+        cudaFreeHost(p->h_err);
+    }
     delete p;
 }
 
@@ -861,7 +877,7 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
     const CUtensorMap &tmap = *tmap_p;
     unsigned grid = (unsigned)std::min<uint32_t>(p.n_tiles, (uint32_t)plan->sm_count);
     long long *d_trace = nullptr;
-    const char *trace_path = (plan->trace_path.empty() || gather || plan->p.n_classes > 16) ? nullptr : plan->trace_path.c_str();   // diagnostics build path
+    const char *trace_path = (plan->trace_path.empty() || gather || plan->p.n_classes > 16 || p.n_wg > (uint32_t)kMaxWG2) ? nullptr : plan->trace_path.c_str();   // diagnostics build path
     if (trace_path) { cudaMalloc(&d_trace, 2048 * sizeof(long long)); cudaMemset(d_trace, 0, 2048 * sizeof(long long)); }
     p.trace = d_trace;
     // Mode 2 drops the grid-dependency wait, i.e. EVERY ordering against the work enqueued before this launch on the stream
@@ -892,9 +908,12 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
         const bool many = p.n_classes > 16;
         cudaError_t e;
 #define BNM_LAUNCH(S, G, M) e = cudaLaunchKernelEx(&cfg, fc_chain_kernel<S, false, G, M>, tmap, p)
-        if (p.n_slots == 1) { if (g) { if (many) BNM_LAUNCH(1, true, true); else BNM_LAUNCH(1, true, false); } else { if (many) BNM_LAUNCH(1, false, true); else BNM_LAUNCH(1, false, false); } }
+#define BNM_LAUNCH4(G, M) e = cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, G, M, false, true>, tmap, p)
+        if (p.n_wg > (uint32_t)kMaxWG2) { if (g) { if (many) BNM_LAUNCH4(true, true); else BNM_LAUNCH4(true, false); } else { if (many) BNM_LAUNCH4(false, true); else BNM_LAUNCH4(false, false); } }
+        else if (p.n_slots == 1) { if (g) { if (many) BNM_LAUNCH(1, true, true); else BNM_LAUNCH(1, true, false); } else { if (many) BNM_LAUNCH(1, false, true); else BNM_LAUNCH(1, false, false); } }
         else { if (g) { if (many) BNM_LAUNCH(2, true, true); else BNM_LAUNCH(2, true, false); } else { if (many) BNM_LAUNCH(2, false, true); else BNM_LAUNCH(2, false, false); } }
 #undef BNM_LAUNCH
+#undef BNM_LAUNCH4
         if (e != cudaSuccess) return -4;
     }
     if (trace_path) {   // diagnostics only: synchronous dump of the phase clocks
@@ -940,7 +959,10 @@ int fc_chain_launch_f32(FcChainPlan *plan, const float *in, size_t n, int32_t *l
     p.off_gstage = 0;
     p.fimages = in;
     p.in_elems = plan->in_bytes;
-    p.n_wg = std::min<uint32_t>(p.n_wg, kFloatWG);
+    if (p.n_wg > kFloatWG) {   // two epilogue warpgroups next to the quantiser warps, two slots each when TMEM allows
+        p.n_wg = kFloatWG;
+        p.n_slots = std::min<uint32_t>(kMaxSlots, (512 / p.tmem_wg_cols) / kFloatWG);
+    }
     p.n_stages = plan->f_n_stages;
     p.off_w = plan->f_off_w;
     p.off_fring = plan->f_off_fring;

@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
     uint32_t spins = 0;
     while (!mbar_try_wait_hint(bar, parity, 20000u)) {
         if (++spins > (1u << 20)) {
-            if (err_flag) atomicExch(err_flag, code);
+            if (err_flag) *reinterpret_cast<volatile int *>(err_flag) = code;
             __threadfence_system();
             asm volatile("trap;");
         }
@@ -63,7 +63,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
     while (!mbar_try_wait_hint(bar, parity, 20000u)) {
         __nanosleep(sleep_ns);
         if (++spins > (1u << 22)) {
-            if (err_flag) atomicExch(err_flag, code);
+            if (err_flag) *reinterpret_cast<volatile int *>(err_flag) = code;
             __threadfence_system();
             asm volatile("trap;");
         }
@@ -88,7 +88,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity, 
     uint32_t spins = 0;
     while (!mbar_try_wait_hint_a(bar_addr, parity, 20000u)) {
         if (++spins > (1u << 20)) {
-            if (err_flag) atomicExch(err_flag, code);
+            if (err_flag) *reinterpret_cast<volatile int *>(err_flag) = code;
             __threadfence_system();
             asm volatile("trap;");
         }
