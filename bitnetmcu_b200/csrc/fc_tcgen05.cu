@@ -48,6 +48,7 @@ struct ChainParams {
     uint32_t w_bytes;                 // weight image bytes (multiple of 16)
     uint32_t off_w;                   // smem offset (from the 1024-aligned base) of the weight image
     uint32_t tmem_wg_cols, tmem_a_off;
+    uint32_t off_a, a_slot_bytes;     // kSmemA: the hidden layers' int8 activations live in shared memory (one [128 x K] buffer per slot)
     uint32_t n_classes;
     uint32_t n_tiles;
     const uint8_t *w_image;
@@ -88,6 +89,9 @@ struct FcChainPlan {
     // one bulk copy per destination (full NVLink packets instead of 8-byte scattered stores): their own ring depth and layout
     uint32_t g_n_stages = 0, g_off_w = 0, g_off_gstage = 0;
     size_t g_smem_bytes = 0;
+    // wide models (kSmemA launches): activations in shared memory, accumulator-only TMEM slots -> one more tile slot
+    uint32_t sa_n_wg = 0, sa_n_stages = 0, sa_off_w = 0, sa_off_a = 0, sa_a_slot_bytes = 0, sa_tmem_wg_cols = 0;
+    size_t sa_smem_bytes = 0;
     // float-input launches: fewer int8 stages, the freed shared memory holds the quantiser warps' float rings
     uint32_t f_n_stages = 0, f_off_w = 0, f_off_fring = 0;
     size_t f_smem_bytes = 0;
@@ -229,6 +233,52 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
     tmem_st_wait();
 }
 
+// hidden-layer epilogue of the kSmemA form: as relunorm_tmem, but the int8 row goes to shared memory in the no-swizzle K-major
+// layout of the weight tiles (per 32-byte K-step a [128 rows x 32 B] block: 8-row groups 256 B apart, the two 16-byte K-chunks
+// of a group 128 B apart), where the next layer's MMAs read it as their A operand (SS form).
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void relunorm_smem(uint32_t d_addr, uint32_t a_slot_addr, uint32_t row, uint32_t n_pad) {
+    int m = 0;
+    const uint32_t n32 = n_pad & ~31u;
+#pragma unroll 1
+    for (uint32_t c = 0; c < n32; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(d_addr + c, v);
+        tmem_ld_wait();
+        m = max16(reinterpret_cast<const uint32_t (&)[16]>(v[0]), m);
+        m = max16(reinterpret_cast<const uint32_t (&)[16]>(v[16]), m);
+    }
+    if (n32 < n_pad) {
+        uint32_t v[16];
+        tmem_ld_x16(d_addr + n32, v);
+        tmem_ld_wait();
+        m = max16(v, m);
+    }
+    const NormCoef k = norm_coef(m);
+    const uint32_t a_row = a_slot_addr + (row >> 3) * 256 + (row & 7) * 16;
+#pragma unroll 1
+    for (uint32_t c = 0; c < n32; c += 32) {
+        uint32_t v[32], w[8];
+        tmem_ld_x32(d_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; q++) w[q] = norm_pack4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], k);
+        st_shared_v4(a_row + c * 128, w[0], w[1], w[2], w[3]);            // K-step c / 32: block of 4096 B
+        st_shared_v4(a_row + c * 128 + 128, w[4], w[5], w[6], w[7]);
+    }
+    if (n32 < n_pad) {   // (the K-step's second chunk multiplies zero weights)
+        uint32_t v[16], w[4];
+        tmem_ld_x16(d_addr + n32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; q++) w[q] = norm_pack4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], k);
+        st_shared_v4(a_row + n32 * 128, w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 //
@@ -271,6 +321,17 @@ __device__ __forceinline__ void issue_layer_ts(const ChainParams &P, int l, uint
             if (leader) umma_i8_ts(d_tmem, a_tmem + k * 8, b0 + bo, idesc, bo != 0);
 }
 
+// layer l > 1, kSmemA form: A = int8 activations in shared memory (relunorm_smem), B = weight tiles
+__device__ __forceinline__ void issue_layer_ss(const ChainParams &P, int l, uint32_t w_base, uint32_t d_tmem, uint32_t a_smem, bool leader) {
+    const uint64_t a0 = make_smem_desc(a_smem, 128, 256, UMMA_LAYOUT_NONE);
+    const uint64_t b0 = make_smem_desc(w_base + P.b_off[l], 128, 256, UMMA_LAYOUT_NONE);
+    const uint32_t b_step = (P.n_pad[l] * 32) >> 4, nk = P.k_steps[l], idesc = P.idesc[l];
+    uint32_t bo = 0;
+    for (uint32_t pl = 0; pl < P.planes[l]; pl++)
+        for (uint32_t k = 0; k < nk; k++, bo += b_step)
+            if (leader) umma_i8_ss(d_tmem, a0 + (uint64_t)(k * (4096 >> 4)), b0 + bo, idesc, bo != 0);
+}
+
 // kManyClasses: more than 16 classes (chunked logits / argmax epilogue).  A template parameter, like kGather, so that the common
 // kernel stays below the 32 kB instruction cache: the gather variant at 41 kB ran 9 % slower for code size alone.
 // kFloatIn: the input scaling of the reference's caller (test_inference.py:140-141: scale = 127 / max(max|x|, 1e-5), q = round-half-even
@@ -278,7 +339,9 @@ __device__ __forceinline__ void issue_layer_ts(const ChainParams &P, int l, uint
 // image, bulk async copies into a small ring), reduce each row's absolute maximum, quantise and write the int8 row
 // straight into the shared-memory image stage in the SWIZZLE_128B layout the layer-1 MMA expects -- the place of the TMA load.
 // Float input then costs 1 024 B of HBM traffic per image once, instead of 1 024 + 256 (quantise kernel) + 256 (this kernel).
-template <int kSlots, bool kTrace, bool kGather, bool kManyClasses, bool kFloatIn = false, bool kFourWG = false>
+// kSmemA: wide models -- the hidden layers' activations go through shared memory instead of TMEM columns (relunorm_smem), so
+// that a tile slot is the accumulator alone and one more slot fits (Binary-160: 3 x 160 columns instead of 2 x 208).
+template <int kSlots, bool kTrace, bool kGather, bool kManyClasses, bool kFloatIn = false, bool kFourWG = false, bool kSmemA = false>
 __global__ void __launch_bounds__(kFloatIn ? kFloatWG * 160 + 32 * kFloatQuantWarps : (kFourWG ? kMaxWG : kMaxWG2) * 160, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -400,7 +463,8 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                         issue_layer1(P, smem_base + s * P.stage_bytes, w_base, d_tmem, leader);
                     } else {
                         tc_fence_after();
-                        issue_layer_ts(P, l, w_base, d_tmem, a_tmem, leader);
+                        if (kSmemA) issue_layer_ss(P, l, w_base, d_tmem, smem_base + P.off_a + v * P.a_slot_bytes, leader);
+                        else issue_layer_ts(P, l, w_base, d_tmem, a_tmem, leader);
                     }
                     if (leader) umma_commit(&bar_mma[g][q]);
                     __syncwarp();
@@ -439,7 +503,8 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                             if (kFloatIn) mbar_arrive(&bar_free[i % n_st]);
                             else issue_tile_load(i + n_st);
                         }
-                        if (n_pad_l == 64) relunorm_tmem64(d_tm, d_tm + a_off);
+                        if (kSmemA) relunorm_smem(d_tm, smem_base + P.off_a + (g * kSlots + q) * P.a_slot_bytes, quarter * 32 + lane, n_pad_l);
+                        else if (n_pad_l == 64) relunorm_tmem64(d_tm, d_tm + a_off);
                         else relunorm_tmem(d_tm, d_tm + a_off, n_pad_l);
                         // this thread's reads of D and writes of A are complete: tell the issuer (128 fire-and-forget arrivals per
                         // step; measured faster than syncwarp + one elected arrival: fewer instructions)
@@ -749,6 +814,28 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
             plan->g_smem_bytes = std::max<size_t>((size_t)plan->g_off_gstage + round_up(gstage, 128) + 1024, 116 * 1024);
         }
     }
+    {   // wide models: with the activations in shared memory a slot is the accumulator alone -- used when that buys a third slot
+        const uint32_t fit = 512 / p.tmem_wg_cols, acc_cols = round_up(d_cols, 32), acc_fit = 512 / acc_cols;
+        uint32_t a_row = 0;
+        for (int l = 1; l < n_layers; l++) a_row = std::max(a_row, p.k_steps[l] * 32);
+        const uint32_t wg = std::min<uint32_t>(kMaxWG2, acc_fit), a_slot = kTileM * a_row;
+        const uint32_t fixed_a = round_up(p.w_bytes, 128) + wg * a_slot;
+        const char *knob = getenv("BNM_SMEM_A");   // tuning knob: 0 = never
+        if (fit <= 2 && acc_fit > fit && n_layers > 1 && p.n_classes <= 16 && !(knob && atoi(knob) == 0) &&
+            fixed_a + 2 * p.stage_bytes <= smem_limit) {
+            plan->sa_n_wg = wg;
+            plan->sa_tmem_wg_cols = acc_cols;
+            plan->sa_a_slot_bytes = a_slot;
+            plan->sa_n_stages = std::min<uint32_t>(6, (smem_limit - fixed_a) / p.stage_bytes);
+            plan->sa_off_w = plan->sa_n_stages * p.stage_bytes;
+            plan->sa_off_a = plan->sa_off_w + round_up(p.w_bytes, 128);
+            plan->sa_smem_bytes = std::max<size_t>((size_t)plan->sa_off_a + wg * a_slot + 1024, 116 * 1024);
+        }
+    }
+    if (getenv("BNM_VERBOSE"))   // diagnostics: the shapes this plan launches
+        fprintf(stderr, "bitnetmcu_b200: fused FC plan: %u warpgroups x %u slots, %u TMEM columns per slot, %u stages, %u weight bytes; "
+                        "smem-activation form: %u warpgroups, %u stages, %zu B smem\n", p.n_wg, p.n_slots, p.tmem_wg_cols, p.n_stages, p.w_bytes,
+                plan->sa_n_wg, plan->sa_n_stages, plan->sa_smem_bytes);
     if (const char *e = getenv("BNM_TRACE")) plan->trace_path = e;                                   // diagnostics, read once
     if (const char *e = getenv("BNM_STAGGER_NS")) plan->stagger_override = (int)(atof(e) * 1.8);     // tuning knob; ~1.8 cycles per ns under load
     for (int j = 0; j < 16; j++) p.kadd[j] = (uint32_t)j < p.n_classes ? 15 - j : -(1 << 30);
@@ -776,7 +863,7 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
     if (cudaDeviceSynchronize() != cudaSuccess) { fc_chain_plan_destroy(plan); return fail("weight image kernel failed"); }
     p.w_image = plan->d_w_image;
     p.err = plan->d_err;
-    const int smem_any = (int)std::max(std::max(plan->smem_bytes, plan->g_smem_bytes), plan->f_smem_bytes);
+    const int smem_any = (int)std::max(std::max(plan->smem_bytes, plan->g_smem_bytes), std::max(plan->f_smem_bytes, plan->sa_smem_bytes));
     if (cudaFuncSetAttribute(fc_chain_kernel<1, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<2, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
@@ -791,6 +878,7 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
         cudaFuncSetAttribute(fc_chain_kernel<1, false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, false, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, false, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
+        cudaFuncSetAttribute(fc_chain_kernel<1, false, false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<1, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess ||
         cudaFuncSetAttribute(fc_chain_kernel<2, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_any) != cudaSuccess) {
         fc_chain_plan_destroy(plan);
@@ -906,10 +994,19 @@ int fc_chain_launch(FcChainPlan *plan, const int8_t *in, size_t n, int32_t *logi
         cfg.numAttrs = plan->overlap ? 1 : 0;
         const bool g = p.n_lab_dst || p.n_log_dst;
         const bool many = p.n_classes > 16;
+        const bool smem_a = !g && !many && plan->sa_smem_bytes != 0;
+        if (smem_a) {
+            p.n_wg = plan->sa_n_wg; p.n_slots = 1;
+            p.tmem_wg_cols = plan->sa_tmem_wg_cols;
+            p.n_stages = plan->sa_n_stages; p.off_w = plan->sa_off_w; p.off_a = plan->sa_off_a; p.a_slot_bytes = plan->sa_a_slot_bytes;
+            cfg.blockDim = dim3(p.n_wg * 160);
+            cfg.dynamicSmemBytes = plan->sa_smem_bytes;
+        }
         cudaError_t e;
 #define BNM_LAUNCH(S, G, M) e = cudaLaunchKernelEx(&cfg, fc_chain_kernel<S, false, G, M>, tmap, p)
 #define BNM_LAUNCH4(G, M) e = cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, G, M, false, true>, tmap, p)
-        if (p.n_wg > (uint32_t)kMaxWG2) { if (g) { if (many) BNM_LAUNCH4(true, true); else BNM_LAUNCH4(true, false); } else { if (many) BNM_LAUNCH4(false, true); else BNM_LAUNCH4(false, false); } }
+        if (smem_a) e = cudaLaunchKernelEx(&cfg, fc_chain_kernel<1, false, false, false, false, false, true>, tmap, p);
+        else if (p.n_wg > (uint32_t)kMaxWG2) { if (g) { if (many) BNM_LAUNCH4(true, true); else BNM_LAUNCH4(true, false); } else { if (many) BNM_LAUNCH4(false, true); else BNM_LAUNCH4(false, false); } }
         else if (p.n_slots == 1) { if (g) { if (many) BNM_LAUNCH(1, true, true); else BNM_LAUNCH(1, true, false); } else { if (many) BNM_LAUNCH(1, false, true); else BNM_LAUNCH(1, false, false); } }
         else { if (g) { if (many) BNM_LAUNCH(2, true, true); else BNM_LAUNCH(2, true, false); } else { if (many) BNM_LAUNCH(2, false, true); else BNM_LAUNCH(2, false, false); } }
 #undef BNM_LAUNCH
