@@ -239,17 +239,36 @@ __device__ __forceinline__ void relunorm_tmem(uint32_t d_addr, uint32_t a_addr, 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 32-column chunks of a TMEM row, software-pipelined: the load of chunk c+1 is in flight while f works on chunk c (the
+// tcgen05.ld latency otherwise sits in front of every chunk: with one slot per warpgroup nothing else hides it)
+template <typename F>
+__device__ __forceinline__ void for_chunks32_pipelined(uint32_t d_addr, uint32_t n32, F f) {
+    if (n32 == 0) return;
+    uint32_t va[32], vb[32];
+    tmem_ld_x32(d_addr, va);
+    tmem_ld_wait();
+    uint32_t c = 0;
+#pragma unroll 1
+    while (true) {
+        if (c + 32 < n32) tmem_ld_x32(d_addr + c + 32, vb);
+        f(va, c);
+        c += 32;
+        if (c >= n32) break;
+        tmem_ld_wait();
+        if (c + 32 < n32) tmem_ld_x32(d_addr + c + 32, va);
+        f(vb, c);
+        c += 32;
+        if (c >= n32) break;
+        tmem_ld_wait();
+    }
+}
 __device__ __forceinline__ void relunorm_smem(uint32_t d_addr, uint32_t a_slot_addr, uint32_t row, uint32_t n_pad) {
     int m = 0;
     const uint32_t n32 = n_pad & ~31u;
-#pragma unroll 1
-    for (uint32_t c = 0; c < n32; c += 32) {
-        uint32_t v[32];
-        tmem_ld_x32(d_addr + c, v);
-        tmem_ld_wait();
+    for_chunks32_pipelined(d_addr, n32, [&](const uint32_t (&v)[32], uint32_t) {
         m = max16(reinterpret_cast<const uint32_t (&)[16]>(v[0]), m);
         m = max16(reinterpret_cast<const uint32_t (&)[16]>(v[16]), m);
-    }
+    });
     if (n32 < n_pad) {
         uint32_t v[16];
         tmem_ld_x16(d_addr + n32, v);
@@ -258,16 +277,13 @@ __device__ __forceinline__ void relunorm_smem(uint32_t d_addr, uint32_t a_slot_a
     }
     const NormCoef k = norm_coef(m);
     const uint32_t a_row = a_slot_addr + (row >> 3) * 256 + (row & 7) * 16;
-#pragma unroll 1
-    for (uint32_t c = 0; c < n32; c += 32) {
-        uint32_t v[32], w[8];
-        tmem_ld_x32(d_addr + c, v);
-        tmem_ld_wait();
+    for_chunks32_pipelined(d_addr, n32, [&](const uint32_t (&v)[32], uint32_t c) {
+        uint32_t w[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) w[q] = norm_pack4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], k);
         st_shared_v4(a_row + c * 128, w[0], w[1], w[2], w[3]);            // K-step c / 32: block of 4096 B
         st_shared_v4(a_row + c * 128 + 128, w[4], w[5], w[6], w[7]);
-    }
+    });
     if (n32 < n_pad) {   // (the K-step's second chunk multiplies zero weights)
         uint32_t v[16], w[4];
         tmem_ld_x16(d_addr + n32, v);
