@@ -462,10 +462,12 @@ def test_processfclayer_on_tcgen05(lib, oracle, enc):
 
 @pytest.mark.parametrize("enc", [2, 4, 12, 16, 20, 64, 1])
 @pytest.mark.parametrize("widths", [(256, 96, 64, 37), (256, 160, 160, 17), (256, 48, 250), (256, 16, 16, 10), (64, 224, 32, 20),
-                                    (256, 64, 64, 64, 64, 64, 64, 64, 10)])
+                                    (256, 64, 64, 64, 64, 64, 64, 64, 10), (256, 160, 144, 10), (256, 256, 10), (128, 176, 176, 176, 7),
+                                    (256, 96, 96, 10)])
 def test_chains_on_tcgen05(lib, oracle, enc, widths):
     """Random-code chains with odd shapes: A-from-TMEM (.ts) layers of every width class (16..224), the wide two-pass
-    ReLUNorm, FP130 with +128 (residual plane) in EVERY layer, > 16 classes, the 8-layer maximum."""
+    ReLUNorm, FP130 with +128 (residual plane) in EVERY layer, > 16 classes, the 8-layer maximum; wide models with <= 16 classes
+    run the shared-memory-activation form (three / two accumulator-only slots, 16-column tails), 96-wide ones four warpgroups."""
     from bitnetmcu_b200 import _lib, pack as P
     from bitnetmcu_b200.engine import Engine
     if enc == 1 and any(w % 32 for w in widths[:-1]):
@@ -475,7 +477,8 @@ def test_chains_on_tcgen05(lib, oracle, enc, widths):
     m = P.random_fc_model(enc, widths, seed=enc + sum(widths))
     m.img_bytes = widths[0]
     rng = np.random.default_rng(sum(widths))
-    imgs = rng.integers(-128, 128, size=(1500 + 11, widths[0])).astype(np.int8)
+    n_img = 148 * 128 * 3 + 11 if widths in ((256, 160, 144, 10), (256, 96, 96, 10)) else 1500 + 11   # several tiles per CTA for the new forms
+    imgs = rng.integers(-128, 128, size=(n_img, widths[0])).astype(np.int8)
     imgs[:50] = np.clip(imgs[:50], 0, 127)
     want, want_lab = oracle.infer(m, imgs)
     e = Engine(m, path=_lib.PATH_TCGEN05)
