@@ -16,6 +16,16 @@ e.set_option(_lib.OPT_PATH, _lib.PATH_LAYERS); a = e.infer(q)
 e.set_option(_lib.OPT_PATH, _lib.PATH_TCGEN05); b = e.infer(q)
 assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 print('layers == tcgen05 on binary160, quantised input ok')
+# four-warpgroup form (2bitsym-96) and the shared-memory-activation form (binary160 above) over several tiles per CTA
+import numpy as _np
+for nm in ('2bitsym96', 'binary160'):
+    e4 = E.Engine(Model.load('tests/golden/models/%s.bnm' % nm))
+    big = _np.random.default_rng(5).integers(-128, 128, size=(148 * 128 * 2 + 9, 256)).astype(_np.int8)
+    e4.set_option(_lib.OPT_PATH, _lib.PATH_LAYERS); a4 = e4.infer(big)
+    e4.set_option(_lib.OPT_PATH, _lib.PATH_TCGEN05); b4 = e4.infer(big)
+    assert _np.array_equal(a4[0], b4[0]) and _np.array_equal(a4[1], b4[1])
+    e4.close()
+print('four-warpgroup and smem-activation forms ok')
 # both CNN front-end kernels on a 48-channel model (tiles that straddle images), emulation mode, fused gather on one GPU
 import torch, ctypes as C
 m48 = Model.load('tests/golden/models/cnn_48.bnm')
@@ -46,5 +56,5 @@ ref = e.infer(E.quantize_images(xf.cpu().numpy()))
 assert np.array_equal(f_log.cpu().numpy(), ref[0])
 print('fused float input ok')
 " > gpurun_out/sanitize_$tool.log 2>&1
-  echo "exit $?"; grep -E "ERROR SUMMARY|smoke|ok$|Error|error" gpurun_out/sanitize_$tool.log | head -12
+  echo "exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke|ok$|Error|error" gpurun_out/sanitize_$tool.log | head -12
 done
