@@ -588,6 +588,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE.json configs)")
+    ap.add_argument("--configs-multi-gpu", action="store_true", help="run the `configs` block at N > 1 as well (default: N = 1 only, "
+                    "they are single-GPU workloads and every one of them synchronises the ranks)")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--sustain-seconds", type=float, default=1.0)
     ap.add_argument("--path", default="auto", choices=["auto", "layers", "tcgen05"])
@@ -728,7 +730,7 @@ def main():
 
     # ---- the other BASELINE.json configs
     configs = None
-    if not args.no_configs:
+    if not args.no_configs and (world == 1 or args.configs_multi_gpu):
         configs = []
         shared = None
         for name, batch in EXTRA_CONFIGS:
@@ -774,7 +776,8 @@ def main():
             "value_overlapped_launches": world * n / (ms_overlap * 1e-3),
             "value_sustained": sustained,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
-            "parity_vs_oracle_sample": parity, "gather": gather, "configs": configs, "latency_us_batch1": latency,
+            "parity_vs_oracle_sample": parity, "gather": gather, "configs": configs,
+            "configs_note": None if configs is not None else "the other BASELINE configs are reported by the N = 1 run", "latency_us_batch1": latency,
         }
         print(json.dumps(out), file=RESULT_OUT, flush=True)
     eng.close()
