@@ -28,7 +28,7 @@ namespace bnm {
 constexpr int kMaxWG = 4;        // epilogue warpgroups: three with 2 tile slots each (6 x (64 D + 16 A) = 480 of the 512 TMEM columns),
                                  // or four with one slot each when only 4..5 slots fit (kFourWG instantiations)
 constexpr int kMaxWG2 = 3;       // ... of the two-slot form
-constexpr int kMaxStages = 7;    // (2 x kMaxStages + 2 x kMaxWG x kMaxSlots + 1 barriers are initialised by one lane each)
+constexpr int kMaxStages = 7;
 constexpr uint32_t kFloatQuantWarps = 8;    // float-input path: quantiser warps per CTA
 constexpr uint32_t kFloatWG = 2;            // ... next to two epilogue warpgroups (four tiles in flight are plenty at 1 kB per image): 576 threads
 constexpr uint32_t kFloatRowsPerWarp = 128 / kFloatQuantWarps;   // rows of every tile per quantiser warp
@@ -311,6 +311,7 @@ __device__ __forceinline__ void relunorm_smem(uint32_t d_addr, uint32_t a_slot_a
 //           ready[g][slot] (128 arrivals: every epilogue thread has written A / finished reading D -> issuer may go on).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 2;
+constexpr uint32_t kFullBars = 4;           // "tile landed" barriers per ring stage (see the ring comment in the kernel)
 constexpr uint32_t kReadyArrivals = 128;   // every epilogue thread arrives
 
 // layer-1 MMAs: A = image tile in smem (SWIZZLE_128B K-major), B = weight tiles.  Whole warp converged so that all
@@ -361,7 +362,7 @@ template <int kSlots, bool kTrace, bool kGather, bool kManyClasses, bool kFloatI
 __global__ void __launch_bounds__(kFloatIn ? kFloatWG * 160 + 32 * kFloatQuantWarps : (kFourWG ? kMaxWG : kMaxWG2) * 160, 1)
 fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[2][kMaxStages], bar_mma[kMaxWG][kMaxSlots], bar_ready[kMaxWG][kMaxSlots];
+    __shared__ __align__(8) uint64_t bar_full[kFullBars][kMaxStages], bar_mma[kMaxWG][kMaxSlots], bar_ready[kMaxWG][kMaxSlots];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bar_w;   // weight image landed (one bulk async copy, no generic-proxy writes)
     __shared__ __align__(8) uint64_t bar_fload[kFloatQuantWarps][2];   // kFloatIn: a quantiser warp's ring slot has landed (bulk async copy)
@@ -395,12 +396,17 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     // phase.  Three slots on two warpgroups: 15 % slower.)  The first n_st loads are
     // issued during setup, right after the weight copy has been requested; afterwards the warp that
     // has just seen the layer-1 MMAs of tile i complete (stage free) refills the stage with tile i + n_st.  Ring round
-    // u = i / n_st signals barrier bar_full[u & 1][s] (phase (u >> 1) & 1): with two barriers per stage a parity wait
-    // stays unambiguous even when a slot runs a whole round ahead of the loads.
+    // u = i / n_st signals barrier bar_full[u % kFullBars][s], phase parity (u / kFullBars) & 1.  A parity wait is only
+    // unambiguous if it starts after the barrier's previous phase has completed: the wait for tile i + kFullBars n_st (same
+    // barrier as tile i, other parity) must come after tile i has landed.  The issuer reaches it after its slot's previous
+    // tile, i + kFullBars n_st - n_virt, has landed; that tile's load was requested after tile i landed iff
+    // n_virt <= (kFullBars - 1) n_st.  With four barriers per stage every shape qualifies (slots may outnumber stages: the
+    // gather launches run 6 slots on 5 stages, the shared-memory-activation form 3 on 2); with two barriers per stage a
+    // development shape with 8 slots on 6 stages lost a phase under launch overlap and trapped on a bounded wait.
     const uint64_t l2_policy = policy_evict_first();   // images are read exactly once
     auto issue_tile_load = [&](uint32_t i) {
         const uint32_t s = i % n_st;
-        uint64_t *bar = &bar_full[(i / n_st) & 1][s];
+        uint64_t *bar = &bar_full[(i / n_st) & (kFullBars - 1)][s];
         mbar_arrive_expect_tx(bar, P.stage_bytes);
         const int32_t row = (int32_t)((tile0 + i * tile_step) * kTileM);
         for (uint32_t a = 0; a < P.in_atoms; a++)
@@ -414,11 +420,15 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     if (kTrace && P.trace && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1024 + 2 * blockIdx.x] = (long long)gt; }
     const bool setup_thread = tid == n_wg * 128;
     if (warp == n_wg * 4) {
-        // barrier init, one lane per barrier (29 mbarrier.init in a row by one thread took ~1100 cycles of every launch)
-        if (lane < 2 * kMaxStages) { if ((lane % kMaxStages) < n_st) mbar_init(&bar_full[lane / kMaxStages][lane % kMaxStages], kFloatIn ? kFloatQuantWarps : 1); }
-        else if (lane < 2 * kMaxStages + kMaxWG * kMaxSlots) mbar_init(&bar_mma[0][0] + (lane - 2 * kMaxStages), 1);
-        else if (lane < 2 * kMaxStages + 2 * kMaxWG * kMaxSlots) mbar_init(&bar_ready[0][0] + (lane - 2 * kMaxStages - kMaxWG * kMaxSlots), kReadyArrivals);
-        else if (lane == 2 * kMaxStages + 2 * kMaxWG * kMaxSlots) mbar_init(&bar_w, 1);
+        // barrier init, at most two barriers per lane (29 mbarrier.init in a row by one thread took ~1100 cycles of every launch)
+        constexpr uint32_t kNFull = kFullBars * kMaxStages, kNSlot = kMaxWG * kMaxSlots;
+#pragma unroll
+        for (uint32_t b = lane; b <= kNFull + 2 * kNSlot; b += 32) {
+            if (b < kNFull) { if ((b % kMaxStages) < n_st) mbar_init(&bar_full[b / kMaxStages][b % kMaxStages], kFloatIn ? kFloatQuantWarps : 1); }
+            else if (b < kNFull + kNSlot) mbar_init(&bar_mma[0][0] + (b - kNFull), 1);
+            else if (b < kNFull + 2 * kNSlot) mbar_init(&bar_ready[0][0] + (b - kNFull - kNSlot), kReadyArrivals);
+            else mbar_init(&bar_w, 1);
+        }
         if (kFloatIn && lane < n_st) mbar_init(&bar_free[lane], 1);
         if (kFloatIn && lane >= 8 && lane < 8 + 2 * kFloatQuantWarps) mbar_init(&bar_fload[(lane - 8) >> 1][lane & 1], 1);
         fence_mbar_init();
@@ -474,7 +484,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                     }
                     if (l == 0) {
                         const uint32_t s = i % n_st;
-                        mbar_wait(&bar_full[(i / n_st) & 1][s], (i / (2 * n_st)) & 1, P.err, 2);
+                        mbar_wait(&bar_full[(i / n_st) & (kFullBars - 1)][s], (i / (kFullBars * n_st)) & 1, P.err, 2);
                         tc_fence_after();
                         issue_layer1(P, smem_base + s * P.stage_bytes, w_base, d_tmem, leader);
                     } else {
@@ -719,7 +729,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
             if (k == kGroupsPerTile - 1) {
                 fence_proxy_async_smem();   // the layer-1 MMAs (async proxy) read what these generic-proxy stores wrote
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_full[(i / n_st) & 1][s]);
+                if (lane == 0) mbar_arrive(&bar_full[(i / n_st) & (kFullBars - 1)][s]);
             }
         }
     }
