@@ -311,8 +311,10 @@ __device__ __forceinline__ void relunorm_smem(uint32_t d_addr, uint32_t a_slot_a
 //           ready[g][slot] (128 arrivals: every epilogue thread has written A / finished reading D -> issuer may go on).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 2;
-constexpr uint32_t kFullBars = 4;           // "tile landed" barriers per ring stage (see the ring comment in the kernel)
+constexpr uint32_t kFullBars = 8;           // "tile landed" barriers per ring stage: >= slots / gcd(slots, stages) for every shape (ring comment in the kernel)
 constexpr uint32_t kReadyArrivals = 128;   // every epilogue thread arrives
+static_assert(kFullBars >= (uint32_t)(kMaxWG * kMaxSlots) && (kFullBars & (kFullBars - 1)) == 0,
+              "kFullBars must cover slots / gcd(slots, stages) for every launch shape (and be a power of two)");
 
 // layer-1 MMAs: A = image tile in smem (SWIZZLE_128B K-major), B = weight tiles.  Whole warp converged so that all
 // descriptor arithmetic stays in the uniform datapath; only the tcgen05 instructions are predicated on one lane.
@@ -397,12 +399,15 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     // issued during setup, right after the weight copy has been requested; afterwards the warp that
     // has just seen the layer-1 MMAs of tile i complete (stage free) refills the stage with tile i + n_st.  Ring round
     // u = i / n_st signals barrier bar_full[u % kFullBars][s], phase parity (u / kFullBars) & 1.  A parity wait is only
-    // unambiguous if it starts after the barrier's previous phase has completed: the wait for tile i + kFullBars n_st (same
-    // barrier as tile i, other parity) must come after tile i has landed.  The issuer reaches it after its slot's previous
-    // tile, i + kFullBars n_st - n_virt, has landed; that tile's load was requested after tile i landed iff
-    // n_virt <= (kFullBars - 1) n_st.  With four barriers per stage every shape qualifies (slots may outnumber stages: the
-    // gather launches run 6 slots on 5 stages, the shared-memory-activation form 3 on 2); with two barriers per stage a
-    // development shape with 8 slots on 6 stages lost a phase under launch overlap and trapped on a bounded wait.
+    // unambiguous if it starts after the barrier's previous phase has completed: the wait for tile j (same barrier as tile
+    // j - kFullBars n_st, other parity) must come after that tile has landed.  What is certain when the issuer gets to tile j:
+    // its slot's earlier tiles j - a n_virt have landed, and with a tile every earlier tile of the same STAGE (a stage's loads
+    // are requested one after the other).  The latest same-stage tile among them is j - m n_st with m = n_virt / gcd(n_virt,
+    // n_st) -- 1 when every slot keeps its stage (6 slots on 6 stages), 6 for the gather launches (6 slots on 5 stages), 4 for
+    // the four-warpgroup form (4 on 5), 3 for the shared-memory-activation form (3 on 2).  So kFullBars >= m for every shape:
+    // 8 covers all of them (n_virt <= 8).  Two barriers per stage, the original scheme, were only safe for m = 1: a development
+    // shape with 8 slots on 6 stages lost a phase under launch overlap and trapped on a bounded wait (tests/test_ring_protocol.py
+    // replays the protocol on a discrete-event model with adversarial load latencies).
     const uint64_t l2_policy = policy_evict_first();   // images are read exactly once
     auto issue_tile_load = [&](uint32_t i) {
         const uint32_t s = i % n_st;
@@ -420,7 +425,7 @@ fc_chain_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     if (kTrace && P.trace && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); P.trace[1024 + 2 * blockIdx.x] = (long long)gt; }
     const bool setup_thread = tid == n_wg * 128;
     if (warp == n_wg * 4) {
-        // barrier init, at most two barriers per lane (29 mbarrier.init in a row by one thread took ~1100 cycles of every launch)
+        // barrier init, at most three barriers per lane (29 mbarrier.init in a row by one thread took ~1100 cycles of every launch)
         constexpr uint32_t kNFull = kFullBars * kMaxStages, kNSlot = kMaxWG * kMaxSlots;
 #pragma unroll
         for (uint32_t b = lane; b <= kNFull + 2 * kNSlot; b += 32) {
@@ -808,7 +813,7 @@ FcChainPlan *fc_chain_plan_create(const FcLayerDev *layers, int n_layers, uint32
         }
         if (const char *e = getenv("BNM_SLOTS")) p.n_slots = p.n_wg <= kMaxWG2 ? std::max(1, std::min<int>((int)std::min<uint32_t>(kMaxSlots, fit / p.n_wg), atoi(e))) : 1;
     }
-    const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*static*/;
+    const uint32_t smem_limit = 227 * 1024 - 1024 /*alignment slack*/ - 1024 /*static: barriers*/;
     p.off_w = 0;  // set below: stages first (1024-aligned), then weights
     uint32_t fixed = round_up(p.w_bytes, 128);
     if (fixed + 2 * p.stage_bytes > smem_limit) { delete plan; return fail("fused path: weights do not fit in shared memory"); }
